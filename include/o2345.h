@@ -1,0 +1,256 @@
+/*
+ * libo2345_sm100.so -- C-ABI of the B200-native (sm_100a) kernels behind One-2-3-45's
+ * SparseNeuS-style reconstruction hot path.
+ *
+ * The reference has no FFI of its own for this path: its boundary is plain Python classes
+ * (SparseSdfNetwork, SparseNeuSRenderer, FeatureNet, GeneralRenderingNetwork, Projector) that
+ * call PyTorch/ATen, torchsparse v1.4.0, inplace_abn and PyMCubes.  Each entry point below
+ * names the reference call site(s) it replaces; INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all floating point data is fp32, dense and contiguous in the stated layout;
+ *   - the caller allocates every buffer (outputs and scratch); nothing is allocated or
+ *     freed behind the ABI and no call synchronises the device;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - return value 0 on success, negative O2345_E* otherwise; o2345_last_error() returns a
+ *     thread-local description of the most recent failure.
+ */
+#ifndef O2345_H_
+#define O2345_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O2345_OK 0
+#define O2345_EINVAL (-1)
+#define O2345_ECUDA (-2)
+#define O2345_EUNSUPPORTED (-3)
+
+#define O2345_ABI_VERSION 1
+
+typedef void* o2345_stream_t;
+
+int o2345_abi_version(void);
+/* Copies the last error message of the calling thread into buf (NUL terminated). */
+int o2345_last_error(char* buf, size_t n);
+/* Fills (major, minor, sm_count) of the current device; fails if it is not sm_100. */
+int o2345_device_info(int* major, int* minor, int* sms);
+
+/* ------------------------------------------------------------------------------------------
+ * B8 / B9 / B10: SDF query = quirky trilinear latent fetch + positional embedding +
+ * weight-normed 39->128->128->128 MLP (+ analytic d sdf / d x).
+ * Replaces SparseSdfNetwork.sdf            reconstruction/models/sparse_sdf_network.py:402-420
+ *          ops.grid_sampler.grid_sample_3d reconstruction/ops/grid_sampler.py:64-216
+ *          LatentSDFLayer.forward          reconstruction/models/sparse_sdf_network.py:111-136
+ *          Embedding.forward               reconstruction/models/embedder.py:81-101
+ *          SparseSdfNetwork.gradient       reconstruction/models/sparse_sdf_network.py:476-499
+ *          extract_fields (lattice mode)   reconstruction/models/sparse_neus_renderer.py:882-905
+ * ------------------------------------------------------------------------------------------ */
+
+/* Number of floats of the packed MLP weights (see o2345_sdf_pack_weights). */
+#define O2345_SDF_PE 39
+#define O2345_SDF_HID 128
+#define O2345_SDF_LAT 16
+#define O2345_SDF_IN1 144
+/* layout (floats): W0t[39][128] b0[128] W1t[144][128] b1[128] W2t[144][128] b2[128]
+ *                  W1[128][144] W0[128][48]   (un-transposed copies for the backward pass)  */
+#define O2345_SDF_PACK_FLOATS (39 * 128 + 128 + 2 * (144 * 128 + 128) + 128 * 144 + 128 * 48)
+
+/* w0 [128,39], w1 [128,144], w2 [128,144] are the EFFECTIVE (weight-normed) matrices,
+ * row-major as nn.Linear stores them; b* the biases.  Writes the packed blob. */
+int o2345_sdf_pack_weights(const float* w0, const float* b0, const float* w1, const float* b1,
+                           const float* w2, const float* b2, float* pack, o2345_stream_t stream);
+
+/* Where the query points come from. */
+#define O2345_PTS_EXPLICIT 0 /* pts [n,3]                                                   */
+#define O2345_PTS_LATTICE 1  /* point i = (lin[i/(R*R)], lin[(i/R)%R], lin[i%R]), n = R^3     */
+#define O2345_PTS_RAYS 2     /* point i = o[r] + d[r] * z[r*z_stride + s], r = i / S, s = i % S */
+
+typedef struct o2345_points {
+  int mode;
+  const float* pts;    /* EXPLICIT: [n,3]                                  */
+  const float* lin;    /* LATTICE: [R] coordinates                          */
+  int R;               /* LATTICE                                           */
+  const float* rays_o; /* RAYS: [n_rays,3]                                  */
+  const float* rays_d; /* RAYS: [n_rays,3]                                  */
+  const float* z;      /* RAYS: depth of sample s on ray r                  */
+  int S;               /* RAYS: samples per ray                             */
+  int z_stride;        /* RAYS: row stride of z in floats                   */
+} o2345_points;
+
+/* vol_cl: conditional volume, channel-last [D,D,D,16] (voxel (x,y,z) -> ((x*D+y)*D+z)*16).
+ * active: optional uint8 [n]; points with active[i]==0 are not evaluated and receive
+ *         sdf = inactive_sdf, feat = 0, latent = 0, grad = 0 (reference
+ *         sparse_neus_renderer.py:135-139, 229-241).
+ * Outputs (any may be NULL): sdf [n], feat [n,127], latent [n,16], grad [n,3].
+ * If negate != 0 the sdf output is written as -sdf (extract_fields' u = -sdf). */
+int o2345_sdf_query(const o2345_points* src, int64_t n, const float* vol_cl, int D, const float* wpack,
+                    const uint8_t* active, float inactive_sdf, int negate, float* sdf, float* feat,
+                    float* latent, float* grad, o2345_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B3 / B4 / B5 / B7: cost-volume build.
+ * Replaces generate_grid + back_project_sparse_type (called twice) + aggregate_multiview_features
+ *          + sparse_to_dense_volume:  reconstruction/ops/generate_grids.py:4-19,
+ *          reconstruction/ops/back_project.py:5-86,
+ *          reconstruction/models/sparse_sdf_network.py:221-284,321-346.
+ * ------------------------------------------------------------------------------------------ */
+
+/* proj [V,4,4] = K @ w2c per view (row-major), origin [3] world position of voxel (0,0,0).
+ * mask_bits[D^3]: bit v set iff voxel is inside view v's frustum (|gx|<=1, |gy|<=1, z>0);
+ * keep[D^3] = popcount(mask) > min_views.  V <= 32. */
+int o2345_frustum_mask(const float* proj, int V, const float* origin, float voxel_size, int D, int sizeH,
+                       int sizeW, int min_views, uint32_t* mask_bits, uint8_t* keep, o2345_stream_t stream);
+
+/* Ordered stream compaction: rows[k] = i of the k-th non-zero flag (ascending i), index[i] = k or -1
+ * (index may be NULL), *count = number kept.  scratch: o2345_compact_scratch_ints(n) int32. */
+int64_t o2345_compact_scratch_ints(int64_t n);
+int o2345_compact(const uint8_t* flags, int64_t n, int32_t* rows, int32_t* index, int32_t* count,
+                  int32_t* scratch, o2345_stream_t stream);
+
+/* feats_nhwc [V,h,w,16] compressed feature maps (channel-last).  For every kept voxel (rows,
+ * *count, at most max_rows) writes cost[row] = [var(16), mean(16)] over the V views; features are
+ * NOT masked, counts come from mask_bits (reference sparse_sdf_network.py:234-245). */
+int o2345_costvol_gather(const float* feats_nhwc, int V, int h, int w, int sizeH, int sizeW, const float* proj,
+                         const float* origin, float voxel_size, int D, const int32_t* rows, const int32_t* count,
+                         int64_t max_rows, const uint32_t* mask_bits, float* cost, o2345_stream_t stream);
+
+/* Scatter rows [n,16] into vol_cl [D^3,16] (channel-last), optionally vol_cf [16,D^3] (the
+ * reference layout [1,16,X,Y,Z]) and occ [D^3] (1.0 where a row exists).  Outputs are zero-filled first. */
+int o2345_dense_scatter(const float* feat, const int32_t* rows, const int32_t* count, int64_t max_rows, int D,
+                        float* vol_cl, float* vol_cf, float* occ, o2345_stream_t stream);
+
+/* Nearest occupancy lookup, ATen grid_sample(mode='nearest', align_corners=False) semantics
+ * (reference sparse_neus_renderer.py:153-169).  out[i] = 1 iff occ at the nearest voxel > 0. */
+int o2345_occ_nearest(const o2345_points* src, int64_t n, const float* occ, int D, uint8_t* out,
+                      o2345_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B6: sparse 3-D convolution stack (torchsparse v1.4.0 semantics) + BatchNorm(batch stats) + ReLU.
+ * Replaces spnn.Conv3d / spnn.BatchNorm / spnn.ReLU as used by SparseCostRegNet:
+ *          reconstruction/tsparse/modules.py:94-124,259-304.
+ * A level is described by a dense lattice index[E^3] (row id or -1), its row list rows[n] (cell
+ * ids, ascending) and a device-side count.  Level l+1 has extent E/2+1.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Flags the cells of the next coarser level (k=3, stride 2 down-sampling rule). cmin_scratch: int32[3]. */
+int o2345_sp_coarsen(const int32_t* fine_index, int Ef, const int32_t* fine_rows, const int32_t* fine_count,
+                     int64_t max_fine, int Ec, uint8_t* coarse_flags, int32_t* cmin_scratch,
+                     o2345_stream_t stream);
+
+/* mode 0: same level; 1: stride-2 down (in = fine, out = coarse); 2: transposed stride-2 (in = coarse,
+ * out = fine).  kernel [27,Cin,Cout] (x-fastest offsets).  Writes raw outputs [rows,Cout] and the
+ * per-channel sum / sum of squares into stats[2*Cout] (float64, zeroed by the call). */
+int o2345_sp_conv(const float* in_feats, const int32_t* in_index, int Ein, const int32_t* out_rows,
+                  const int32_t* out_count, int64_t max_out, int Eout, int mode, const float* kernel, int Cin,
+                  int Cout, float* out_raw, double* stats, o2345_stream_t stream);
+
+/* out = relu(batchnorm(x; batch stats, gamma, beta, eps)) (+ skip).  out may alias x. */
+int o2345_sp_bn_relu(const float* x, const int32_t* count, int64_t max_rows, int C, const double* stats,
+                     const float* gamma, const float* beta, float eps, const float* skip, float* out,
+                     o2345_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B10: marching cubes on the dense u = -sdf grid.
+ * Replaces mcubes.marching_cubes(u, 0): reconstruction/models/sparse_neus_renderer.py:932.
+ * Case tables come from the host (o2345/mc_tables.py): tri_table int8[256,16], n_tri uint8[256],
+ * edge_owner int8[12,4] = (dx,dy,dz,axis) of the lattice edge that carries cell edge e.
+ * ------------------------------------------------------------------------------------------ */
+int o2345_mc_classify(const float* u, int R, float iso, uint8_t* cases, uint8_t* cell_flags, uint8_t* edge_flags,
+                      o2345_stream_t stream);
+int o2345_mc_vertices(const float* u, int R, float iso, const int32_t* edges, const int32_t* count,
+                      int64_t max_verts, double* verts, o2345_stream_t stream);
+int64_t o2345_scan_scratch_ints(int64_t n);
+int o2345_mc_tri_offsets(const uint8_t* cases, const int32_t* cells, const int32_t* count, int64_t max_cells,
+                         const uint8_t* n_tri_table, int32_t* offsets, int32_t* total, int32_t* scratch,
+                         o2345_stream_t stream);
+int o2345_mc_triangles(const uint8_t* cases, int R, const int32_t* cells, const int32_t* count, int64_t max_cells,
+                       const int32_t* tri_offsets, const int8_t* tri_table, const uint8_t* n_tri_table,
+                       const int8_t* edge_owner, const int32_t* vert_index, int32_t* tris, o2345_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B1 / B2: FeatureNet + compress layer primitives.
+ * Replaces nn.Conv2d + InPlaceABN + F.interpolate in reconstruction/models/featurenet.py:12-91,
+ *          reconstruction/models/trainer_generic.py:1104-1125, sparse_sdf_network.py:171-173.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct o2345_view4 {
+  float* ptr;               /* element (n,c,h,w) lives at ptr[n*sn + (c+c0)*sc + h*sh + w*sw] */
+  int64_t sn, sc, sh, sw;
+  int c0;
+} o2345_view4;
+
+/* in [N,Cin,H,W] NCHW, weight [Cout,Cin,K,K], bias NULL or [Cout]; out NCHW raw.  If stats != NULL the
+ * per-channel sum / sum of squares of the output are accumulated into stats[2*Cout] (zeroed first). */
+int o2345_conv2d(const float* in, int N, int Cin, int H, int W, const float* weight, const float* bias, int Cout,
+                 int K, int stride, int pad, float* out, double* stats, o2345_stream_t stream);
+/* InPlaceABN forward with batch statistics: (x-mean)/sqrt(var+eps)*(|gamma|+eps)+beta, leaky-ReLU(slope). */
+int o2345_abn_apply(const float* x, int N, int C, int H, int W, const double* stats, const float* gamma,
+                    const float* beta, float eps, float slope, const o2345_view4* out, o2345_stream_t stream);
+/* Bilinear up-sampling by an integer factor, align_corners=True, optional add [N,C,H*f,W*f]. */
+int o2345_upsample_bilinear(const float* x, int N, int C, int H, int W, int factor, const float* add,
+                            const o2345_view4* out, o2345_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B11 - B14: volume rendering.
+ * Replaces SparseNeuSRenderer.up_sample / cat_z_vals / render_core / render
+ *              reconstruction/models/sparse_neus_renderer.py:73-151,171-455,457-635
+ *          sample_pdf, sample_ptsFeatures_from_feature{Volume,Maps}
+ *              reconstruction/models/render_utils.py:8-120
+ *          Projector.compute / compute_view_independent / compute_angle*
+ *              reconstruction/models/projector.py:15-62,96-425
+ *          GeneralRenderingNetwork.forward
+ *              reconstruction/models/rendering_network.py:75-129
+ * ------------------------------------------------------------------------------------------ */
+
+/* One importance round: new_z [R,n_new] drawn by deterministic inverse-CDF sampling (u [n_new] =
+ * linspace(0.5/n, 1-0.5/n, n)) from the NeuS section weights of the current samples z/sdf [R,S]. */
+int o2345_ray_upsample(const float* rays_o, const float* rays_d, int64_t R, const float* z, const float* sdf,
+                       int S, float inv_s, const float* occ, int D, const float* u, int n_new, float* new_z,
+                       o2345_stream_t stream);
+/* Merge the sorted lists (z,sdf) [R,S] and (new_z,new_sdf) [R,n_new] into out_* [R,S+n_new]. */
+int o2345_ray_merge(const float* z, const float* sdf, int S, const float* new_z, const float* new_sdf, int n_new,
+                    int64_t R, float* out_z, float* out_sdf, o2345_stream_t stream);
+/* mid_z = z + dists/2, dists = forward differences (last = sample_dist), active = nearest occupancy. */
+int o2345_ray_midpoints(const float* rays_o, const float* rays_d, int64_t R, const float* z, int S,
+                        float sample_dist, const float* occ, int D, float* mid_z, float* dists, uint8_t* active,
+                        o2345_stream_t stream);
+
+#define O2345_MAP_CH 60 /* channel-last source maps: rgb(3) + pyramid features(56) + 1 pad */
+#define O2345_RNET_PACK_FLOATS 19664
+
+typedef struct o2345_views {
+  int V, H, W;          /* source views and map size                                        */
+  const float* maps;    /* [V,H,W,60] channel-last: [0..2] colour, [3..58] features, [59] 0  */
+  const float* proj;    /* [V,3,4] = intrinsics @ w2c[:3,:4]                                 */
+  const float* centers; /* [V,3] camera centres (c2w translation)                           */
+  float sizeW, sizeH;   /* img_wh used to normalise pixel coordinates                       */
+} o2345_views;
+
+/* Per sample point: geometry feature, per-view colour+feature fetch, ray-difference, view-blending
+ * MLP -> rgb [n,3]; nvalid [n] = number of views whose mask is set (may be NULL).  dir_mode 0: target
+ * direction = normalised (query_center - p) (Projector.compute); 1: dirs [n,3] given
+ * (compute_view_independent, surface normals).  rnet_pack: O2345_RNET_PACK_FLOATS floats, every
+ * matrix stored [in][out] in the order documented in csrc/render.cu. */
+int o2345_render_blend(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl,
+                       const float* occ, int D, const o2345_views* views, int dir_mode, const float* query_center,
+                       const float* dirs, const float* rnet_pack, float* rgb, int32_t* nvalid,
+                       o2345_stream_t stream);
+
+/* NeuS alpha from (sdf, grad), transmittance, colour/depth compositing.  Outputs: color [R,3], depth [R],
+ * optional weights [R,S], cdf [R,S], alpha [R,S], weights_sum [R], color_mask [R] (uint8). */
+int o2345_ray_composite(const float* rays_d, int64_t R, int S, const float* mid_z, const float* dists,
+                        const float* sdf, const float* grad, const float* color, const uint8_t* active,
+                        const int32_t* nvalid, float inv_s, float alpha_inter_ratio, int has_background,
+                        float background, float* color_out, float* depth_out, float* weights_out, float* cdf_out,
+                        float* alpha_out, float* weights_sum_out, uint8_t* color_mask_out, o2345_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* O2345_H_ */

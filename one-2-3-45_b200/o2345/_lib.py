@@ -1,0 +1,112 @@
+"""ctypes binding of libo2345_sm100.so (the C-ABI declared in include/o2345.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails this module
+raises, it never routes work to PyTorch or to the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libo2345_sm100.so")
+
+c_fp = C.c_void_p  # device pointers travel as integers
+c_i64 = C.c_int64
+
+
+class Points(C.Structure):
+    _fields_ = [("mode", C.c_int), ("pts", c_fp), ("lin", c_fp), ("R", C.c_int), ("rays_o", c_fp),
+                ("rays_d", c_fp), ("z", c_fp), ("S", C.c_int), ("z_stride", C.c_int)]
+
+
+class View4(C.Structure):
+    _fields_ = [("ptr", c_fp), ("sn", c_i64), ("sc", c_i64), ("sh", c_i64), ("sw", c_i64), ("c0", C.c_int)]
+
+
+class Views(C.Structure):
+    _fields_ = [("V", C.c_int), ("H", C.c_int), ("W", C.c_int), ("maps", c_fp), ("proj", c_fp),
+                ("centers", c_fp), ("sizeW", C.c_float), ("sizeH", C.c_float)]
+
+
+PTS_EXPLICIT, PTS_LATTICE, PTS_RAYS = 0, 1, 2
+SDF_PACK_FLOATS = 39 * 128 + 128 + 2 * (144 * 128 + 128) + 128 * 144 + 128 * 48
+RNET_PACK_FLOATS = 19664
+MAP_CH = 60
+
+_SIGS = {
+    "o2345_abi_version": (C.c_int, []),
+    "o2345_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "o2345_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "o2345_sdf_pack_weights": (C.c_int, [c_fp] * 7 + [c_fp]),
+    "o2345_sdf_query": (C.c_int, [C.POINTER(Points), c_i64, c_fp, C.c_int, c_fp, c_fp, C.c_float, C.c_int,
+                                  c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_frustum_mask": (C.c_int, [c_fp, C.c_int, c_fp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, c_fp,
+                                     c_fp, c_fp]),
+    "o2345_compact_scratch_ints": (c_i64, [c_i64]),
+    "o2345_compact": (C.c_int, [c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_costvol_gather": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, C.c_float,
+                                       C.c_int, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp]),
+    "o2345_dense_scatter": (C.c_int, [c_fp, c_fp, c_fp, c_i64, C.c_int, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_occ_nearest": (C.c_int, [C.POINTER(Points), c_i64, c_fp, C.c_int, c_fp, c_fp]),
+    "o2345_sp_coarsen": (C.c_int, [c_fp, C.c_int, c_fp, c_fp, c_i64, C.c_int, c_fp, c_fp, c_fp]),
+    "o2345_sp_conv": (C.c_int, [c_fp, c_fp, C.c_int, c_fp, c_fp, c_i64, C.c_int, C.c_int, c_fp, C.c_int, C.c_int,
+                                c_fp, c_fp, c_fp]),
+    "o2345_sp_bn_relu": (C.c_int, [c_fp, c_fp, c_i64, C.c_int, c_fp, c_fp, c_fp, C.c_float, c_fp, c_fp, c_fp]),
+    "o2345_mc_classify": (C.c_int, [c_fp, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_mc_vertices": (C.c_int, [c_fp, C.c_int, C.c_float, c_fp, c_fp, c_i64, c_fp, c_fp]),
+    "o2345_scan_scratch_ints": (c_i64, [c_i64]),
+    "o2345_mc_tri_offsets": (C.c_int, [c_fp, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_mc_triangles": (C.c_int, [c_fp, C.c_int, c_fp, c_fp, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_conv2d": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, C.c_int, C.c_int, C.c_int,
+                               C.c_int, c_fp, c_fp, c_fp]),
+    "o2345_abn_apply": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_float, C.c_float,
+                                  C.POINTER(View4), c_fp]),
+    "o2345_upsample_bilinear": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp,
+                                          C.POINTER(View4), c_fp]),
+    "o2345_ray_upsample": (C.c_int, [c_fp, c_fp, c_i64, c_fp, c_fp, C.c_int, C.c_float, c_fp, C.c_int, c_fp,
+                                     C.c_int, c_fp, c_fp]),
+    "o2345_ray_merge": (C.c_int, [c_fp, c_fp, C.c_int, c_fp, c_fp, C.c_int, c_i64, c_fp, c_fp, c_fp]),
+    "o2345_ray_midpoints": (C.c_int, [c_fp, c_fp, c_i64, c_fp, C.c_int, C.c_float, c_fp, C.c_int, c_fp, c_fp,
+                                      c_fp, c_fp]),
+    "o2345_render_blend": (C.c_int, [C.POINTER(Points), c_i64, c_fp, c_fp, c_fp, C.c_int, C.POINTER(Views),
+                                     C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_ray_composite": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float,
+                                      C.c_float, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+}
+
+EXPORTED = tuple(_SIGS)
+_lib = None
+
+
+class O2345Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise O2345Error(f"{LIB_PATH} is missing: run `python one-2-3-45_b200/build.py` "
+                             "(there is no CPU or PyTorch fallback for this path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    load().o2345_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def call(name, *args):
+    """Calls an int-returning entry point and raises O2345Error on a negative status."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise O2345Error(f"{name} failed with {rc}: {last_error()}")
+    return rc

@@ -109,7 +109,7 @@ def tables():
                 loop.append(e)
                 e = nxt[e]
             for k in range(1, len(loop) - 1):
-                tris.append((loop[0], loop[k], loop[k + 1]))
+                tris.append((loop[0], loop[k + 1], loop[k]))  # wound so that normals leave the inside
         assert len(tris) <= 5, (case, tris)
         n_tri[case] = len(tris)
         flat = [v for t in tris for v in t]

@@ -1,0 +1,114 @@
+"""Scene samples (row B0) and network assembly for the reconstruction path.
+
+`load_sample` mirrors BlenderPerView.__getitem__ (reference data/One2345_eval_new_data.py:139-377)
+for a folder written by run.py (pose.json, stage1_8/0.png, stage2_8/*.png); `synthetic_sample`
+builds the same dict from seeded inputs.  `build_networks` mirrors Runner.__init__ (reference
+exp_runner_generic_blender_val.py:93-151) for the lod-0 demo configuration.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import synthetic as S
+from .featurenet import FeatureNet
+from .rendering_network import GeneralRenderingNetwork, SingleVarianceNetwork
+from .sparse_sdf_network import SparseSdfNetwork
+from .trainer_generic import GenericTrainer
+
+
+class Conf(dict):
+    """pyhocon-like view of the few conf entries the inference path reads."""
+
+    def get_int(self, key, default=None):
+        return int(self.get(key, default))
+
+    def get_float(self, key, default=None):
+        return float(self.get(key, default))
+
+    def get_bool(self, key, default=None):
+        return bool(self.get(key, default))
+
+
+def build_networks(device, vol_dim=96, states=None, n_samples=64, n_importance=64, perturb=1.0, base_exp_dir=None,
+                   variance_init=0.3):
+    """FeatureNet, SparseSdfNetwork, SingleVarianceNetwork, GeneralRenderingNetwork, GenericTrainer on `device`
+    with the constants of reference confs/one2345_lod0_val_demo.conf:66-129 (voxel_size = 2/(D-1))."""
+    fnet = FeatureNet()
+    sdf = SparseSdfNetwork(lod=0, ch_in=56, voxel_size=2.0 / (vol_dim - 1), vol_dims=[vol_dim] * 3, hidden_dim=128,
+                           cost_type='variance_mean', d_pyramid_feature_compress=16, regnet_d_out=16,
+                           num_sdf_layers=4, multires=6)
+    var = SingleVarianceNetwork(variance_init)
+    rnet = GeneralRenderingNetwork(in_geometry_feat_ch=16, in_rendering_feat_ch=56, anti_alias_pooling=True)
+    if states is not None:
+        load = lambda m, sd: m.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in sd.items()}, strict=False)
+        for m, key in ((fnet, "pyramid_feature_network"), (sdf, "sdf_network_lod0"), (rnet, "rendering_network_lod0"),
+                       (var, "variance_network_lod0")):
+            res = load(m, states[key])
+            assert not res.unexpected_keys, res.unexpected_keys
+            assert all("num_batches_tracked" in k for k in res.missing_keys), res.missing_keys
+    for m in (fnet, sdf, var, rnet):
+        m.to(device)
+        for p in m.parameters():
+            p.requires_grad_(False)
+    conf = Conf({"general.base_exp_dir": base_exp_dir, "model.num_lods": 1})
+    trainer = GenericTrainer(None, fnet, None, sdf, None, var, None, rnet, None, n_samples, n_importance, 64, 64, 0,
+                             perturb, alpha_type='div', conf=conf, base_exp_dir=base_exp_dir)
+    return trainer
+
+
+def _sample_from(cams, imgs, device, H, W, pin=False):
+    """Adds the batch dimension the reference's DataLoader adds and moves everything to `device`."""
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+    rays_o, rays_v = S.query_rays(cams["query_intrinsic"], cams["query_c2w"], H, W)
+    host = {
+        "images": t(imgs[1:])[None], "query_image": t(imgs[0])[None], "w2cs": t(cams["w2cs"])[None],
+        "c2ws": t(cams["c2ws"])[None], "intrinsics": t(cams["intrinsics"])[None],
+        "affine_mats": t(cams["affine_mats"])[None], "query_c2w": t(cams["query_c2w"])[None],
+        "query_w2c": t(cams["query_w2c"])[None], "query_near_far": t(cams["query_near_far"])[None],
+        "scale_mat": t(cams["scale_mat"])[None], "trans_mat": t(cams["trans_mat"])[None],
+        "partial_vol_origin": t(cams["partial_vol_origin"])[None], "img_wh": torch.tensor([[W, H]]),
+    }
+    rays = {"rays_o": t(rays_o)[None], "rays_v": t(rays_v)[None]}
+    if pin:
+        host = {k: v.pin_memory() for k, v in host.items()}
+        rays = {k: v.pin_memory() for k, v in rays.items()}
+    sample = {k: v.to(device, non_blocking=pin) for k, v in host.items()}
+    sample["rays"] = {k: v.to(device, non_blocking=pin) for k, v in rays.items()}
+    sample["batch_idx"], sample["meta"] = torch.tensor([0]), ["synthetic"]
+    return sample, host, rays
+
+
+def synthetic_sample(device, n_views=32, H=256, W=256, seed=1234, elev=60.0):
+    """One scene with seeded images: 1 query view + n_views source views."""
+    meta = S.pose_json(elev)
+    k = np.array(meta["intrinsics"])
+    k[:2] *= W / 256.0
+    meta["intrinsics"] = k.tolist()
+    cams = S.scene_cameras(meta, n_src=n_views, img_wh=(W, H))
+    imgs = S.images(n_views + 1, H, W, seed=seed)
+    return _sample_from(cams, imgs, device, H, W)[0]
+
+
+def load_sample(folder, device):
+    """Reads <folder>/pose.json, stage1_8/<first id>, stage2_8/<ids 8..39> like the reference dataset."""
+    from PIL import Image
+    meta = json.load(open(os.path.join(folder, "pose.json")))
+    ids = list(meta["c2ws"].keys())
+
+    def read(path):
+        a = np.asarray(Image.open(path), np.float32) / 255.0
+        a = a.transpose(2, 0, 1)
+        if a.shape[0] == 4:
+            a = a[:3] * a[-1:] + (1 - a[-1:])
+        return a
+
+    imgs = [read(os.path.join(folder, "stage1_8", ids[0]))]
+    imgs += [read(os.path.join(folder, "stage2_8", ids[v])) for v in range(8, 40)]
+    imgs = np.stack(imgs).astype(np.float32)
+    H, W = imgs.shape[2:]
+    cams = S.scene_cameras(meta, n_src=32, img_wh=(W, H))
+    return _sample_from(cams, imgs, device, H, W)[0]

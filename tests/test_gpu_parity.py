@@ -1,0 +1,321 @@
+"""GPU parity: every kernel of the reconstruction path, called through the C-ABI, against the CPU
+oracle on identical seeded inputs (mini configuration) and against the golden vectors frozen from the
+real reference; plus size-independent properties at the full 96^3 / 256^2 configuration.
+
+Tolerances (fp32 everywhere; integer / occupancy outputs must be bit-exact):
+  sdf / latent / features 5e-5 abs, gradient 2e-4 abs, cost volume 5e-4 (E[f^2]-E[f]^2 cancellation),
+  sparse-conv volume 2e-4, colours 1e-3, depth / weights 2e-3 (hierarchical sampling amplifies ulps).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import MINI, OracleMini
+from oracle import recon_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def om():
+    return OracleMini()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def tr(dev):
+    from o2345 import synthetic as S
+    from o2345.pipeline import build_networks
+    return build_networks(dev, vol_dim=MINI["D"], states=S.all_states(0), perturb=0.0)
+
+
+@pytest.fixture(scope="module")
+def gpu(om, tr, dev):
+    """Feature maps and conditional volume computed by the CUDA path."""
+    fm = tr.obtain_pyramid_feature_maps(om.imgs.to(dev))
+    cond = tr.sdf_network_lod0.get_conditional_volume(fm[None], om.origin.to(dev)[None], om.proj.to(dev)[None],
+                                                      sizeH=MINI["H"], sizeW=MINI["W"])
+    torch.cuda.synchronize()
+    return {"fm": fm, "cond": cond, "last": tr.sdf_network_lod0._last}
+
+
+def maxerr(a, b):
+    return float((torch.as_tensor(a).double().cpu() - torch.as_tensor(b).double().cpu()).abs().max())
+
+
+def test_device_is_sm100():
+    import ctypes as C
+    from o2345 import _lib
+    ma, mi, sms = C.c_int(), C.c_int(), C.c_int()
+    _lib.call("o2345_device_info", C.byref(ma), C.byref(mi), C.byref(sms))
+    assert ma.value == 10 and sms.value >= 100
+
+
+def test_feature_net(om, gpu, golden):
+    assert maxerr(gpu["fm"], om.fmaps) < 5e-5
+    assert maxerr(gpu["fm"].flatten()[::37], golden["fmaps_s"]) < 5e-5
+
+
+def test_compress_layer(om, gpu):
+    ref = O.compress_features(om.fmaps, om.st["sdf_network_lod0"]).permute(0, 2, 3, 1)
+    assert maxerr(gpu["last"]["feats_nhwc"], ref) < 1e-4
+
+
+def test_frustum_mask_bit_exact(om, gpu, golden):
+    bits = gpu["last"]["mask_bits"].cpu().numpy().astype(np.uint32)
+    V = MINI["V"]
+    mask = ((bits[:, None] >> np.arange(V)[None, :]) & 1).astype(np.int8)
+    assert np.array_equal(mask, golden["mask"])                      # the REAL reference's mask
+    assert np.array_equal(mask, om.cv["mask"].numpy().astype(np.int8))
+    keep = gpu["last"]["keep"].cpu().numpy().astype(bool)
+    assert np.array_equal(keep, om.cv["keep"].numpy())
+    n = int(gpu["last"]["count"].item())
+    assert n == int(keep.sum())
+    assert np.array_equal(gpu["last"]["rows"][:n].cpu().numpy(), np.nonzero(keep)[0])   # ascending lattice order
+
+
+def test_cost_volume(om, gpu, golden):
+    n = int(gpu["last"]["count"].item())
+    cost = gpu["last"]["cost"][:n]
+    assert maxerr(cost, om.cv["cost"]) < 5e-4
+    assert maxerr(cost.flatten()[::11], golden["cost_s"]) < 5e-4
+
+
+def test_sparse_conv_stack(om, tr, gpu, dev):
+    """Sparse U-Net alone, fed with the oracle's cost rows (isolates B6 from upstream rounding)."""
+    from o2345 import ops
+    n = int(gpu["last"]["count"].item())
+    D = MINI["D"]
+    cost = torch.zeros(D ** 3, 32, device=dev)
+    cost[:n] = om.cv["cost"].to(dev)
+    lvl = ops.SparseLevel(D, gpu["last"]["rows"], gpu["last"]["index"], gpu["last"]["count"], D ** 3)
+    reg = tr.sdf_network_lod0.sparse_costreg_net(cost, lvl)
+    assert maxerr(reg[:n], om.cv["rows"]) < 2e-4
+
+
+def test_dense_volume_and_occupancy(om, gpu, golden):
+    vol, occ = gpu["cond"]["dense_volume_scale0"], gpu["cond"]["valid_mask_volume_scale0"]
+    assert vol.shape == (1, 16, MINI["D"], MINI["D"], MINI["D"])
+    assert np.array_equal(occ.cpu().numpy().astype(np.int8).reshape(-1), golden["occ"])   # bit-exact
+    assert maxerr(vol, om.volume) < 5e-4
+    assert maxerr(vol.flatten()[::13], golden["dense_s"]) < 5e-4
+    cl = vol._o2345_cl[1]
+    assert torch.equal(cl.permute(3, 0, 1, 2), vol[0])
+
+
+def test_sdf_query_and_gradient(om, tr, dev, golden):
+    net = tr.sdf_network_lod0
+    vol = om.volume.to(dev)
+    out = net.sdf(om.pts.to(dev), vol, 0)
+    s, f, l = O.sdf_query(om.pts, om.volume, om.st["sdf_network_lod0"])
+    assert maxerr(out["sampled_latent_scale0"], l) < 5e-6
+    assert maxerr(out["sdf_pts_scale0"], s) < 5e-5
+    assert maxerr(out["sdf_features_pts_scale0"], f) < 5e-5
+    g = net.gradient(om.pts.to(dev), vol, 0)
+    assert g.shape == (om.pts.shape[0], 1, 3)
+    assert maxerr(g[:, 0], O.sdf_gradient(om.pts, om.volume, om.st["sdf_network_lod0"])) < 2e-4
+    # against the real reference (its volume differs by ~1.5e-5)
+    assert maxerr(out["sdf_pts_scale0"], golden["sdf"]) < 1e-4
+    assert maxerr(g[:, 0], golden["grad"]) < 5e-4
+
+
+def test_sdf_ragged_sizes_and_active_mask(om, tr, dev):
+    from o2345 import ops
+    net = tr.sdf_network_lod0
+    vol_cl = om.volume[0].permute(1, 2, 3, 0).contiguous().to(dev)
+    pack = net.sdf_layer.packed()
+    ref = O.sdf_query(om.pts, om.volume, om.st["sdf_network_lod0"])[0]
+    for n in (1, 127, 128, 129, 1000):
+        out = ops.sdf_query(ops.PointSource.explicit(om.pts[:n].to(dev)), vol_cl, pack)["sdf"]
+        assert maxerr(out, ref[:n]) < 5e-5
+    act = (torch.arange(1000) % 3 == 0).to(torch.uint8)
+    out = ops.sdf_query(ops.PointSource.explicit(om.pts[:1000].to(dev)), vol_cl, pack, active=act.to(dev), want_grad=True)
+    exp = torch.where(act.bool()[:, None], ref[:1000], torch.full_like(ref[:1000], 100.0))
+    assert maxerr(out["sdf"], exp) < 5e-5
+    assert float(out["grad"][~act.bool().to(dev)].abs().max()) == 0.0
+    none = ops.sdf_query(ops.PointSource.explicit(om.pts[:300].to(dev)), vol_cl, pack,
+                         active=torch.zeros(300, dtype=torch.uint8, device=dev))["sdf"]
+    assert torch.all(none == 100.0)
+    empty = ops.sdf_query(ops.PointSource.explicit(om.pts[:0].to(dev)), vol_cl, pack)["sdf"]
+    assert empty.shape == (0, 1)
+
+
+def test_nearest_occupancy_bit_exact(om, dev, golden):
+    from o2345 import ops
+    out = ops.occ_nearest(ops.PointSource.explicit(om.pts.to(dev)), om.occ.to(dev))
+    assert np.array_equal(out.cpu().numpy().astype(np.int8), golden["occ_nearest"])
+
+
+def _render(tr, om, dev, vol, occ, fm):
+    return tr.sdf_renderer_lod0.render(
+        om.rays_o.to(dev), om.rays_d.to(dev), om.near.to(dev), om.far.to(dev), tr.sdf_network_lod0,
+        tr.rendering_network_lod0, perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
+        conditional_volume=vol, conditional_valid_mask_volume=occ, feature_maps=fm, color_maps=om.imgs.to(dev),
+        w2cs=om.w2cs.to(dev), intrinsics=om.intr.to(dev), img_wh=[MINI["W"], MINI["H"]], query_c2w=om.qc2w.to(dev))
+
+
+def test_render_against_oracle_same_volume(om, tr, dev):
+    """Ray marcher alone: both sides consume the ORACLE's volume and feature maps."""
+    res = _render(tr, om, dev, om.volume.to(dev), om.occ.to(dev), om.fmaps.to(dev))
+    st = om.st
+    ref = O.render_rays(om.rays_o, om.rays_d, om.near, om.far, om.volume, om.occ, om.fmaps, om.imgs, om.w2cs, om.intr,
+                        om.qc2w, st["sdf_network_lod0"], st["rendering_network_lod0"],
+                        st["variance_network_lod0"]["variance"], W=MINI["W"], H=MINI["H"])
+    assert maxerr(res["z_vals"], ref["z"]) < 1e-4
+    assert maxerr(res["color_fine"], ref["color"]) < 1e-3
+    assert maxerr(res["depth"], ref["depth"]) < 2e-3
+    assert maxerr(res["weights"], ref["weights"]) < 2e-3
+    assert torch.equal(res["color_fine_mask"].cpu(), ref["color_mask"])
+    assert torch.equal(res["inside_sphere"].cpu(), ref["inside"])
+    assert float((res["gradients"].cpu() - ref["gradients"]).abs().mean()) < 1e-4
+
+
+def test_render_end_to_end_against_reference_golden(om, tr, gpu, dev, golden):
+    res = _render(tr, om, dev, gpu["cond"]["dense_volume_scale0"], gpu["cond"]["valid_mask_volume_scale0"], gpu["fm"])
+    assert maxerr(res["color_fine"], golden["color"]) < 2e-3
+    assert maxerr(res["depth"], golden["depth"]) < 5e-3
+    assert maxerr(res["weights"], golden["weights"]) < 5e-3
+    for k in ("depth", "color_fine", "color_fine_mask", "variance", "cdf_fine", "depth_variance", "weights_sum",
+              "weights_max", "alpha_sum", "alpha_mean", "gradients", "weights", "gradient_error_fine",
+              "inside_sphere", "sdf", "sdf_random", "weights_sum_fg"):
+        assert res[k] is not None
+
+
+def test_vertex_colors(om, tr, dev, golden):
+    rgb, nrm = tr.sdf_renderer_lod0.blend_points(
+        om.verts.to(dev), tr.sdf_network_lod0, tr.rendering_network_lod0, om.volume.to(dev), om.occ.to(dev),
+        om.fmaps.to(dev), om.imgs.to(dev), om.w2cs.to(dev), om.intr.to(dev), [MINI["W"], MINI["H"]])
+    col, n_ref = O.vertex_colors(om.verts, om.volume, om.occ, om.fmaps, om.imgs, om.w2cs, om.intr,
+                                 om.st["sdf_network_lod0"], om.st["rendering_network_lod0"], W=MINI["W"], H=MINI["H"])
+    assert maxerr(nrm, n_ref) < 2e-4
+    assert maxerr(rgb, col) < 1e-3
+    assert maxerr(rgb, golden["vert_color"]) < 2e-3
+
+
+def test_marching_cubes_bit_exact_cases_and_vertex_set(om, tr, dev, golden):
+    from o2345 import ops
+    R = MINI["R"]
+    u = torch.from_numpy(golden["u_grid"]).to(dev)
+    verts, tris, cases = ops.marching_cubes(u, 0.0)
+    v_ref, t_ref, c_ref = O.marching_cubes(golden["u_grid"], 0.0)
+    assert np.array_equal(cases.cpu().numpy(), c_ref)                       # bit-exact case grid
+    assert np.array_equal(verts.cpu().numpy(), v_ref)                       # same order, same float64 values
+    t = tris.cpu().numpy().astype(np.int64)
+    key = lambda a: np.sort(np.sort(a, 1).view([("a", a.dtype), ("b", a.dtype), ("c", a.dtype)]).ravel())
+    assert np.array_equal(key(np.ascontiguousarray(t)), key(np.ascontiguousarray(t_ref)))
+
+
+def test_extract_geometry_matches_oracle_grid(om, tr, dev, golden):
+    R = MINI["R"]
+    v, t, u = tr.sdf_renderer_lod0.extract_geometry(tr.sdf_network_lod0, torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3),
+                                                    R, 0.0, dev, conditional_volume=om.volume.to(dev), lod=0)
+    assert maxerr(u, O.sdf_grid(om.volume, om.st["sdf_network_lod0"], R)) < 5e-5
+    assert maxerr(u, golden["u_grid"]) < 1e-4
+    assert v.dtype == np.float64 and np.all(np.abs(v) <= 1.0 + 1e-9) and t.min() >= 0 and t.max() < len(v)
+
+
+def test_export_mesh_end_to_end(tr, dev, tmp_path):
+    from o2345.pipeline import synthetic_sample
+    tr.base_exp_dir = str(tmp_path)
+    sample = synthetic_sample(dev, n_views=MINI["V"], H=MINI["H"], W=MINI["W"])
+    out = tr(sample, mode="export_mesh", resolution=48)
+    assert (tmp_path / "mesh.ply").exists()
+    v, t = out["vertices"], out["triangles"]
+    assert len(v) > 100 and len(t) > 100 and out["colors"].shape == (len(v), 3)
+    e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), 1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert cnt.max() <= 2                                                   # manifold
+
+
+# ----------------------------------------------------------------------------------------------
+# full-size properties (96^3 volume, 32 views of 256^2, BASELINE configs[1] reconstruction part)
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full(dev):
+    from o2345 import synthetic as S
+    from o2345.pipeline import build_networks, synthetic_sample
+    tr = build_networks(dev, vol_dim=96, states=S.all_states(0), perturb=0.0)
+    sample = synthetic_sample(dev, n_views=32, H=256, W=256)
+    imgs, fmaps, cond, W, H = tr._conditional_features(sample)
+    torch.cuda.synchronize()
+    return tr, sample, imgs, fmaps, cond
+
+
+def test_full_size_volume_properties(full):
+    tr, sample, imgs, fmaps, cond = full
+    vol, occ = cond["dense_volume_scale0"], cond["valid_mask_volume_scale0"]
+    last = tr.sdf_network_lod0._last
+    n = int(last["count"].item())
+    assert 0.5 * 96 ** 3 < n < 96 ** 3                       # ~86 % of the lattice at the demo camera layout
+    assert float(occ.sum()) == n                             # occupancy == kept voxels, bit-exact
+    rows = last["rows"][:n]
+    assert torch.all(rows[1:] > rows[:-1])                   # ascending lattice order
+    bits = last["mask_bits"].long() & 0xFFFFFFFF
+    pop = sum(((bits >> v) & 1) for v in range(32))
+    assert torch.equal(pop > 1, last["keep"].bool())        # frustum rule: seen by >= 2 views
+    assert torch.isfinite(vol).all()
+    assert torch.all(vol[0][:, occ[0, 0] == 0] == 0)        # untouched voxels stay zero
+    assert float(vol.min()) >= 0.0                           # U-Net ends in ReLU + ReLU-skip sum
+
+
+def test_full_size_sdf_lattice_matches_explicit_points(full, dev):
+    """Lattice mode (extract_fields) == explicit-point mode on the same coordinates; linearity checks of the
+    gradient against central differences."""
+    from o2345 import ops
+    tr, sample, imgs, fmaps, cond = full
+    net = tr.sdf_network_lod0
+    vol = cond["dense_volume_scale0"]
+    R = 64
+    u = tr.sdf_renderer_lod0.extract_fields([-1] * 3, [1] * 3, R, None, dev, conditional_volume=vol, lod=0)
+    lin = torch.linspace(-1, 1, R, device=dev)
+    idx = torch.randint(0, R, (4096, 3), device=dev)
+    pts = torch.stack([lin[idx[:, 0]], lin[idx[:, 1]], lin[idx[:, 2]]], -1)
+    s = net.sdf(pts, vol, 0)["sdf_pts_scale0"][:, 0]
+    assert torch.equal(-u[idx[:, 0], idx[:, 1], idx[:, 2]], s)
+    p = (torch.rand(4096, 3, device=dev) * 1.6 - 0.8)
+    g = net.gradient(p, vol, 0)[:, 0]
+    h = 1e-3
+    fd = torch.stack([(net.sdf(p + h * e, vol, 0)["sdf_pts_scale0"] - net.sdf(p - h * e, vol, 0)["sdf_pts_scale0"])[:, 0] / (2 * h)
+                      for e in torch.eye(3, device=dev)], -1)
+    assert float((g - fd).abs().median()) < 5e-3
+
+
+def test_full_size_render_properties(full, dev):
+    tr, sample, imgs, fmaps, cond = full
+    ro = sample["rays"]["rays_o"][0][::37][:2048]
+    rd = sample["rays"]["rays_v"][0][::37][:2048]
+    near, far = sample["query_near_far"][0, :1], sample["query_near_far"][0, 1:]
+    out = tr.sdf_renderer_lod0.render(ro, rd, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0,
+                                      perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
+                                      conditional_volume=cond["dense_volume_scale0"],
+                                      conditional_valid_mask_volume=cond["valid_mask_volume_scale0"],
+                                      feature_maps=fmaps, color_maps=imgs, w2cs=sample["w2cs"][0],
+                                      intrinsics=sample["intrinsics"][0], img_wh=[256, 256], query_c2w=sample["query_c2w"])
+    z, w = out["z_vals"], out["weights"]
+    assert z.shape == (2048, 128) and torch.all(z[:, 1:] >= z[:, :-1])       # sortedness after 4 merges
+    assert torch.all(w >= 0) and torch.all(out["weights_sum"] <= 1.0 + 1e-4)
+    assert torch.all(w[out["inside_sphere"] == 0] == 0)                      # masked samples carry no weight
+    c = out["color_fine"]
+    assert torch.isfinite(c).all() and float(c.min()) >= -1e-4 and float(c.max()) <= 1.0 + 1e-4
+    # idempotence / determinism: the same chunk rendered twice is bit-identical
+    out2 = tr.sdf_renderer_lod0.render(ro, rd, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0,
+                                       perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
+                                       conditional_volume=cond["dense_volume_scale0"],
+                                       conditional_valid_mask_volume=cond["valid_mask_volume_scale0"],
+                                       feature_maps=fmaps, color_maps=imgs, w2cs=sample["w2cs"][0],
+                                       intrinsics=sample["intrinsics"][0], img_wh=[256, 256], query_c2w=sample["query_c2w"])
+    assert torch.equal(out2["color_fine"], c) and torch.equal(out2["z_vals"], z)
+    # chunking invariance: two half chunks == one chunk
+    h = 1024
+    a = tr.sdf_renderer_lod0.render(ro[:h], rd[:h], near, far, tr.sdf_network_lod0, tr.rendering_network_lod0,
+                                    perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
+                                    conditional_volume=cond["dense_volume_scale0"],
+                                    conditional_valid_mask_volume=cond["valid_mask_volume_scale0"],
+                                    feature_maps=fmaps, color_maps=imgs, w2cs=sample["w2cs"][0],
+                                    intrinsics=sample["intrinsics"][0], img_wh=[256, 256], query_c2w=sample["query_c2w"])
+    assert torch.equal(a["color_fine"], c[:h])

@@ -1,0 +1,85 @@
+"""CPU: host-side logic that needs no GPU -- case tables, seeded inputs, state-dict layout, PLY writer."""
+import os
+
+import numpy as np
+import torch
+
+from o2345 import mc_tables, synthetic as S
+
+
+def test_mc_tables_are_consistent():
+    mask, tri, ntri = mc_tables.tables()
+    assert ntri[0] == 0 and ntri[255] == 0 and ntri.max() <= 5
+    for c in range(256):
+        used = set(int(e) for e in tri[c] if e >= 0)
+        want = {e for e in range(12) if ((c >> mc_tables.EDGE_ENDS[e, 0]) & 1) != ((c >> mc_tables.EDGE_ENDS[e, 1]) & 1)}
+        assert used == want and mask[c] == sum(1 << e for e in want)
+        # complementary cases cut the same edges with the same number of triangles or a re-pairing of them
+        assert mask[c] == mask[255 - c]
+
+
+def test_marching_cubes_sphere_is_closed_and_outward():
+    from oracle import recon_oracle as O
+    R = 24
+    g = np.linspace(-1, 1, R)
+    x, y, z = np.meshgrid(g, g, g, indexing="ij")
+    u = 0.6 - np.sqrt(x * x + y * y + z * z)          # u > 0 inside (u = -sdf)
+    v, t, _ = O.marching_cubes(u.astype(np.float32), 0.0)
+    e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), 1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert np.all(cnt == 2)                              # watertight
+    assert len(v) - len(cnt) + len(t) == 2               # Euler characteristic of a sphere
+    p = v[t]
+    vol = np.einsum("ij,ij->i", p[:, 0], np.cross(p[:, 1], p[:, 2])).sum() / 6.0
+    assert vol > 0                                       # normals point outwards
+
+
+def test_synthetic_is_deterministic_and_shaped():
+    a, b = S.all_states(0), S.all_states(0)
+    for k in a:
+        for kk in a[k]:
+            assert np.array_equal(a[k][kk], b[k][kk])
+    sd = a["sdf_network_lod0"]
+    assert sd["sdf_layer.lin0.weight_v"].shape == (128, 39) and sd["sdf_layer.lin2.weight_v"].shape == (128, 144)
+    assert sd["sparse_costreg_net.conv6.net.0.kernel"].shape == (27, 64, 64)
+    cams = S.scene_cameras()
+    assert cams["affine_mats"].shape == (32, 4, 4) and cams["query_near_far"][0] < 0 < cams["query_near_far"][1]
+
+
+def test_host_modules_accept_reference_state_dicts():
+    from o2345.pipeline import build_networks
+    tr = build_networks("cpu", vol_dim=24, states=S.all_states(0))
+    keys = set(tr.sdf_network_lod0.state_dict().keys())
+    for k in S.sdf_network_state(0):
+        assert k in keys
+    assert set(S.feature_net_state(1)) <= set(tr.pyramid_feature_network_geometry_lod0.state_dict().keys())
+    assert set(S.rendering_network_state(2)) == set(tr.rendering_network_lod0.state_dict().keys())
+    w = tr.sdf_network_lod0.sdf_layer.lin1.effective()
+    v, g = torch.from_numpy(S.sdf_network_state(0)["sdf_layer.lin1.weight_v"]), torch.from_numpy(S.sdf_network_state(0)["sdf_layer.lin1.weight_g"])
+    assert torch.allclose(w, v * (g / v.norm(dim=1, keepdim=True)))
+
+
+def test_rendering_network_pack_layout():
+    from o2345.rendering_network import GeneralRenderingNetwork
+    from o2345 import _lib
+    net = GeneralRenderingNetwork(16, 56, True)
+    net.load_state_dict({k: torch.as_tensor(v) for k, v in S.rendering_network_state(2).items()})
+    p = net.packed()
+    assert p.numel() == _lib.RNET_PACK_FLOATS
+    # base_fc.0 block starts after ray_dir_fc: [193][64] stored input-major
+    off = 64 + 16 + 1024 + 64
+    assert torch.equal(p[off:off + 193 * 64].view(193, 64), net.base_fc[0].weight.t())
+    assert float(p[-4]) == abs(float(net.s))
+
+
+def test_ply_writer(tmp_path):
+    from o2345.trainer_generic import write_ply
+    v = np.random.rand(5, 3)
+    f = np.array([[0, 1, 2], [2, 3, 4]])
+    c = (np.random.rand(5, 3) * 255).astype(np.uint8)
+    path = os.path.join(tmp_path, "m.ply")
+    write_ply(path, v, f, c)
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n")
+    assert b"element vertex 5" in head and b"element face 2" in head
+    assert len(body) == 5 * 16 + 2 * 13
