@@ -455,14 +455,14 @@ extern "C" int o2345_sdf_pack_weights(const float* w0, const float* b0, const fl
 extern "C" int o2345_sdf_query(const o2345_points* src, int64_t n, const float* vol_cl, int D,
                                const float* wpack, const uint8_t* active, float inactive_sdf, int negate,
                                float* sdf, float* feat, float* latent, float* grad, o2345_stream_t stream) {
+  O2345_CHECK_ARG(n >= 0, "negative point count");
+  if (n == 0) return O2345_OK;
   O2345_CHECK_ARG(src && vol_cl && wpack, "null pointer");
   O2345_CHECK_ARG(D >= 2 && D <= 1024, "volume side out of range");
-  O2345_CHECK_ARG(n >= 0, "negative point count");
   if (src->mode == O2345_PTS_EXPLICIT) O2345_CHECK_ARG(src->pts, "explicit points missing");
   else if (src->mode == O2345_PTS_LATTICE) O2345_CHECK_ARG(src->lin && src->R > 0 && n == (int64_t)src->R * src->R * src->R, "bad lattice");
   else if (src->mode == O2345_PTS_RAYS) O2345_CHECK_ARG(src->rays_o && src->rays_d && src->z && src->S > 0 && src->z_stride >= src->S && n % src->S == 0, "bad ray source");
   else O2345_CHECK_ARG(false, "unknown point source mode");
-  if (n == 0) return O2345_OK;
   static bool attr_done = false;
   if (!attr_done) {
     O2345_CUDA(cudaFuncSetAttribute(sdf_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));

@@ -104,9 +104,26 @@ def last_error() -> str:
     return buf.value.decode(errors="replace")
 
 
+# kernels launched per successful entry-point call (memsets are not counted)
+_KERNELS_PER_CALL = {"o2345_compact": 3, "o2345_sp_coarsen": 3, "o2345_mc_tri_offsets": 4}
+_launches = 0
+
+
+def reset_launches():
+    global _launches
+    _launches = 0
+
+
+def launches() -> int:
+    """Number of o2345 kernels launched since reset_launches() (bench.py's gpu_launches)."""
+    return _launches
+
+
 def call(name, *args):
     """Calls an int-returning entry point and raises O2345Error on a negative status."""
+    global _launches
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise O2345Error(f"{name} failed with {rc}: {last_error()}")
+    _launches += _KERNELS_PER_CALL.get(name, 1)
     return rc
