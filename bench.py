@@ -299,7 +299,7 @@ def cpu_baseline(tr, sample, budget_rays=48):
     ro = sample['rays']['rays_o'][0].reshape(-1, 3).cpu()[sel]
     rd = sample['rays']['rays_v'][0].reshape(-1, 3).cpu()[sel]
     near, far = sample['query_near_far'][0, :1].cpu(), sample['query_near_far'][0, 1:].cpu()
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     w0 = time.perf_counter()
     O.render_rays(ro, rd, near, far, vol, occ, fmaps.cpu(), imgs.cpu(), sample['w2cs'][0].cpu(), sample['intrinsics'][0].cpu(),
                   sample['query_c2w'].cpu(), st["sdf_network_lod0"], st["rendering_network_lod0"],
@@ -307,6 +307,12 @@ def cpu_baseline(tr, sample, budget_rays=48):
     dt = time.perf_counter() - w0
     return {"value": budget_rays / dt / 1e6, "unit": "M rays/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{budget_rays} rays x (64+64) samples x {N_VIEWS} views of the same image, volume + feature maps prebuilt ({dt:.1f} s)"}
+
+
+def host_threads():
+    """Threads for the CPU arm: every core up to 32 (the torch-CPU port stops scaling, and on a 128-thread
+    host gets slower, beyond that; the count actually used is what the JSON reports as `cores`)."""
+    return max(1, min(os.cpu_count() or 1, 32))
 
 
 def run_reference(args):
@@ -317,7 +323,7 @@ def run_reference(args):
     from helpers import states_torch
     from o2345 import synthetic as S
     from oracle import recon_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     st = states_torch(0)
     cams = S.scene_cameras(S.pose_json(60.0), n_src=N_VIEWS, img_wh=(W, H))
     imgs = torch.from_numpy(S.images(N_VIEWS + 1, H, W, seed=1234))[1:]

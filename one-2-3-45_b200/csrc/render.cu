@@ -176,7 +176,7 @@ constexpr int P_TOTAL = P_S + 4;
 static_assert(P_TOTAL == O2345_RNET_PACK_FLOATS, "header and kernel disagree on the rendering-net pack");
 
 constexpr int WS_F = 32 * 64;               // per-warp: cached per-view features [32][64]
-constexpr int WS_X = 256;                   // per-warp: activation scratch
+constexpr int WS_X = 512;                   // per-warp: two [64][4] activation buffers
 constexpr int WS_RGB = 32 * 4;              // per-warp: rgb of each view
 constexpr int WS_TOTAL = WS_F + WS_X + WS_RGB;
 constexpr int BLEND_SMEM = (P_TOTAL + BW * WS_TOTAL) * 4;
@@ -194,6 +194,27 @@ __device__ __forceinline__ void matvec(const float* __restrict__ W, const float*
     float xi = x[i];
     y0 = fmaf(xi, W[i * LD + l0], y0);
     if (OUT > 32) y1 = fmaf(xi, W[i * LD + l1], y1);
+  }
+}
+
+// Four views at once: xs[i*4 + q] is input i of view q.  y0[q] (output `lane`) and y1[q] (output
+// lane+32, OUT > 32 only) start from init0 / init1; each weight is loaded once for the four views.
+template <int IN, int OUT, int LD>
+__device__ __forceinline__ void matvec4(const float* __restrict__ W, const float* __restrict__ xs, int lane,
+                                        float init0, float init1, float (&y0)[4], float (&y1)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) y0[q] = init0, y1[q] = init1;
+  const int l0 = lane < OUT ? lane : 0;
+  const int l1 = (OUT > 32 && lane + 32 < OUT) ? lane + 32 : 0;
+#pragma unroll 4
+  for (int i = 0; i < IN; ++i) {
+    float4 x = *reinterpret_cast<const float4*>(xs + 4 * i);
+    float w0 = W[i * LD + l0];
+    y0[0] = fmaf(x.x, w0, y0[0]), y0[1] = fmaf(x.y, w0, y0[1]), y0[2] = fmaf(x.z, w0, y0[2]), y0[3] = fmaf(x.w, w0, y0[3]);
+    if (OUT > 32) {
+      float w1 = W[i * LD + l1];
+      y1[0] = fmaf(x.x, w1, y1[0]), y1[1] = fmaf(x.y, w1, y1[1]), y1[2] = fmaf(x.z, w1, y1[2]), y1[3] = fmaf(x.w, w1, y1[3]);
+    }
   }
 }
 
@@ -340,36 +361,57 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
       continue;
     }
 
-    // ---- pass A over the valid views: fetch, direction feature, weighted mean
+    // ---- pass A over the valid views, four at a time: fetch, direction feature, weighted mean
     float mean0 = 0.f, mean1 = 0.f;
-    int slot = 0;
-    for (unsigned m = valid; m; m &= m - 1, ++slot) {
-      int v = __ffs(m) - 1;
-      float vgx = __shfl_sync(0xffffffffu, gx, v), vgy = __shfl_sync(0xffffffffu, gy, v);
-      float w = __shfl_sync(0xffffffffu, wv, v);
-      float f0, f1;
-      fetch_map(views.maps + (int64_t)v * H * W * CM, H, W, vgx, vgy, lane, f0, f1);
-      if (lane < 3) sRGB[slot * 4 + lane] = f0;
-      // ray_dir_fc: 4 -> 16 -> 59, ELU after both (reference rendering_network.py:44-47,88)
-      float r0 = __shfl_sync(0xffffffffu, rd0, v), r1 = __shfl_sync(0xffffffffu, rd1, v);
-      float r2 = __shfl_sync(0xffffffffu, rd2, v), r3 = __shfl_sync(0xffffffffu, rd3, v);
-      float hd = 0.f;
-      if (lane < 16)
-        hd = eluf_(sP[P_D0B + lane] + r0 * sP[P_D0W + lane] + r1 * sP[P_D0W + 16 + lane] + r2 * sP[P_D0W + 32 + lane] + r3 * sP[P_D0W + 48 + lane]);
-      float d0 = sP[P_D1B + lane], d1 = sP[P_D1B + 32 + lane];
+    float* sA4 = sX;            // [<=64][4] activations, view-interleaved
+    float* sB4 = sX + 256;      // second buffer
+    for (int g0 = 0; g0 < nvalid; g0 += 4) {
+      int vid[4];
+      float wq[4], f0[4], f1[4];
+      {
+        unsigned m = valid;
+        for (int k = 0; k < g0; ++k) m &= m - 1;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float hi = __shfl_sync(0xffffffffu, hd, i);
-        d0 = fmaf(hi, sP[P_D1W + i * 64 + lane], d0);
-        d1 = fmaf(hi, sP[P_D1W + i * 64 + 32 + lane], d1);
+        for (int q = 0; q < 4; ++q) {
+          vid[q] = m ? __ffs(m) - 1 : -1;
+          m &= m - 1;
+        }
       }
-      f0 += eluf_(d0);
-      f1 = (lane + 32 < NF) ? f1 + eluf_(d1) : 0.f;
-      sF[slot * 64 + lane] = f0;
-      sF[slot * 64 + 32 + lane] = f1;
-      mean0 = fmaf(w, f0, mean0);
-      mean1 = fmaf(w, f1, mean1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int vq = vid[q] >= 0 ? vid[q] : 0;
+        wq[q] = vid[q] >= 0 ? __shfl_sync(0xffffffffu, wv, vq) : 0.f;
+        float vgx = __shfl_sync(0xffffffffu, gx, vq), vgy = __shfl_sync(0xffffffffu, gy, vq);
+        fetch_map(views.maps + (int64_t)vq * H * W * CM, H, W, vgx, vgy, lane, f0[q], f1[q]);
+        float r0 = __shfl_sync(0xffffffffu, rd0, vq), r1 = __shfl_sync(0xffffffffu, rd1, vq);
+        float r2 = __shfl_sync(0xffffffffu, rd2, vq), r3 = __shfl_sync(0xffffffffu, rd3, vq);
+        if (lane == 0) sA4[0 * 4 + q] = r0, sA4[1 * 4 + q] = r1, sA4[2 * 4 + q] = r2, sA4[3 * 4 + q] = r3;
+      }
+      __syncwarp();
+      // ray_dir_fc: 4 -> 16 -> 59, ELU after both (reference rendering_network.py:44-47,88)
+      float hd[4], dmy[4], d0[4], d1[4];
+      matvec4<4, 16, 16>(sP + P_D0W, sA4, lane, lane < 16 ? sP[P_D0B + lane] : 0.f, 0.f, hd, dmy);
+      if (lane < 16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sB4[lane * 4 + q] = eluf_(hd[q]);
+      }
+      __syncwarp();
+      matvec4<16, 64, 64>(sP + P_D1W, sB4, lane, sP[P_D1B + lane], sP[P_D1B + 32 + lane], d0, d1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (g0 + q < nvalid) {
+          if (lane < 3) sRGB[(g0 + q) * 4 + lane] = f0[q];
+          float a0 = f0[q] + eluf_(d0[q]);
+          float a1 = (lane + 32 < NF) ? f1[q] + eluf_(d1[q]) : 0.f;
+          sF[(g0 + q) * 64 + lane] = a0;
+          sF[(g0 + q) * 64 + 32 + lane] = a1;
+          mean0 = fmaf(wq[q], a0, mean0);
+          mean1 = fmaf(wq[q], a1, mean1);
+        }
+      }
+      __syncwarp();
     }
+    int slot = 0;
     // ---- pass B: weighted variance around the mean
     float var0 = 0.f, var1 = 0.f;
     slot = 0;
@@ -392,72 +434,87 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
     matvec<134, 64, 64>(sP + P_B0W, sP + P_B0B, sX, lane, hs0, hs1);
     __syncwarp();
 
-    // ---- per valid view: the rest of the network -> blending logit
+    // ---- groups of four valid views share every weight load (4 independent FMA chains per output)
     float logit = -3.4e38f;  // lane v keeps the logit of view v
-    slot = 0;
-    for (unsigned m = valid; m; m &= m - 1, ++slot) {
-      int v = __ffs(m) - 1;
-      float w = __shfl_sync(0xffffffffu, wv, v);
-      // base_fc[0] per-view part + ELU
-      float a0 = hs0, a1 = hs1;
+    for (int g0 = 0; g0 < nvalid; g0 += 4) {
+      int vid[4];
+      float wq[4];
       {
-        const float* xf = sF + slot * 64;
-        const float* Wf = sP + P_B0W + 134 * 64;
-#pragma unroll 4
-        for (int i = 0; i < NF; ++i) {
-          float xi = xf[i];
-          a0 = fmaf(xi, Wf[i * 64 + lane], a0);
-          a1 = fmaf(xi, Wf[i * 64 + 32 + lane], a1);
+        unsigned m = valid;
+        for (int k = 0; k < g0; ++k) m &= m - 1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          vid[q] = m ? __ffs(m) - 1 : -1;
+          wq[q] = vid[q] >= 0 ? __shfl_sync(0xffffffffu, wv, vid[q]) : 0.f;
+          m &= m - 1;
         }
       }
-      sX[lane] = eluf_(a0), sX[32 + lane] = eluf_(a1);
+      // base_fc[0], per-view part: x1 = elu(hs + Wf . f_v)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        bool on = g0 + q < nvalid;
+        sA4[lane * 4 + q] = on ? sF[(g0 + q) * 64 + lane] : 0.f;
+        sA4[(lane + 32) * 4 + q] = on ? sF[(g0 + q) * 64 + 32 + lane] : 0.f;
+      }
       __syncwarp();
-      float x2, dummy;
-      matvec<64, 32, 32>(sP + P_B1W, sP + P_B1B, sX, lane, x2, dummy);
-      x2 = eluf_(x2);
+      float y0[4], y1[4];
+      matvec4<NF, 64, 64>(sP + P_B0W + 134 * 64, sA4, lane, hs0, hs1, y0, y1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sB4[lane * 4 + q] = eluf_(y0[q]), sB4[(lane + 32) * 4 + q] = eluf_(y1[q]);
       __syncwarp();
-      // vis_fc(x * weight): 32 -> 32 -> 33
-      sX[lane] = x2 * w;
+      // base_fc[2]: 64 -> 32
+      float x2[4], dmy[4];
+      matvec4<64, 32, 32>(sP + P_B1W, sB4, lane, sP[P_B1B + lane], 0.f, x2, dmy);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x2[q] = eluf_(x2[q]), sA4[lane * 4 + q] = x2[q] * wq[q];
       __syncwarp();
-      float hv;
-      matvec<32, 32, 32>(sP + P_V0W, sP + P_V0B, sX, lane, hv, dummy);
-      hv = eluf_(hv);
+      // vis_fc(x * weight): 32 -> 32 -> (32 residual + 1 visibility)
+      float hv[4];
+      matvec4<32, 32, 32>(sP + P_V0W, sA4, lane, sP[P_V0B + lane], 0.f, hv, dmy);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hv[q] = eluf_(hv[q]), sB4[lane * 4 + q] = hv[q];
       __syncwarp();
-      sX[lane] = hv;
-      __syncwarp();
-      float res;
-      matvec<32, 32, 32>(sP + P_V1W, sP + P_V1B, sX, lane, res, dummy);
-      res = eluf_(res);
-      float visr = eluf_(warp_sum(hv * sP[P_V1V + lane]) + sP[P_V1VB]);
-      float vis = sigmoidf_(visr);  // mask is 1 for the views processed here
-      float x3 = x2 + res;
+      float res[4], x3[4], vis[4];
+      matvec4<32, 32, 32>(sP + P_V1W, sB4, lane, sP[P_V1B + lane], 0.f, res, dmy);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float visr = eluf_(warp_sum(hv[q] * sP[P_V1V + lane]) + sP[P_V1VB]);
+        vis[q] = sigmoidf_(visr);                       // mask is 1 for the views processed here
+        x3[q] = x2[q] + eluf_(res[q]);
+        sA4[lane * 4 + q] = x3[q] * vis[q];
+      }
       __syncwarp();
       // vis_fc2(x * vis): 32 -> 32 -> 1, sigmoid
-      sX[lane] = x3 * vis;
+      float h2[4];
+      matvec4<32, 32, 32>(sP + P_U0W, sA4, lane, sP[P_U0B + lane], 0.f, h2, dmy);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float vis2 = sigmoidf_(warp_sum(eluf_(h2[q]) * sP[P_U1W + lane]) + sP[P_U1B]);
+        // rgb_fc input [x(32), vis(1), ray_diff(4)]
+        sB4[lane * 4 + q] = x3[q];
+        int vq = vid[q] >= 0 ? vid[q] : 0;
+        float r0 = __shfl_sync(0xffffffffu, rd0, vq), r1 = __shfl_sync(0xffffffffu, rd1, vq);
+        float r2 = __shfl_sync(0xffffffffu, rd2, vq), r3 = __shfl_sync(0xffffffffu, rd3, vq);
+        if (lane == 0) {
+          sB4[32 * 4 + q] = vis2;
+          sB4[33 * 4 + q] = r0, sB4[34 * 4 + q] = r1, sB4[35 * 4 + q] = r2, sB4[36 * 4 + q] = r3;
+        }
+      }
       __syncwarp();
-      float h2;
-      matvec<32, 32, 32>(sP + P_U0W, sP + P_U0B, sX, lane, h2, dummy);
-      h2 = eluf_(h2);
-      float vis2 = sigmoidf_(warp_sum(h2 * sP[P_U1W + lane]) + sP[P_U1B]);
+      float q1[4];
+      matvec4<37, 16, 16>(sP + P_R0W, sB4, lane, lane < 16 ? sP[P_R0B + lane] : 0.f, 0.f, q1, dmy);
+      if (lane < 16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sA4[lane * 4 + q] = eluf_(q1[q]);
+      }
       __syncwarp();
-      // rgb_fc([x, vis, ray_diff]): 37 -> 16 -> 8 -> 1
-      sX[lane] = x3;
-      if (lane == 0) sX[32] = vis2;
-      float r0 = __shfl_sync(0xffffffffu, rd0, v), r1 = __shfl_sync(0xffffffffu, rd1, v);
-      float r2 = __shfl_sync(0xffffffffu, rd2, v), r3 = __shfl_sync(0xffffffffu, rd3, v);
-      if (lane == 0) { sX[33] = r0; sX[34] = r1; sX[35] = r2; sX[36] = r3; }
-      __syncwarp();
-      float q1;
-      matvec<37, 16, 16>(sP + P_R0W, sP + P_R0B, sX, lane, q1, dummy);
-      q1 = eluf_(q1);
-      __syncwarp();
-      if (lane < 16) sX[64 + lane] = q1;
-      __syncwarp();
-      float q2;
-      matvec<16, 8, 8>(sP + P_R1W, sP + P_R1B, sX + 64, lane, q2, dummy);
-      q2 = (lane < 8) ? eluf_(q2) * sP[P_R2W + lane] : 0.f;
-      float lg = warp_sum(q2) + sP[P_R2B];
-      if (lane == v) logit = lg;
+      float q2[4];
+      matvec4<16, 8, 8>(sP + P_R1W, sA4, lane, lane < 8 ? sP[P_R1B + lane] : 0.f, 0.f, q2, dmy);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lg = warp_sum(lane < 8 ? eluf_(q2[q]) * sP[P_R2W + lane] : 0.f) + sP[P_R2B];
+        if (lane == vid[q]) logit = lg;
+      }
       __syncwarp();
     }
     // ---- softmax over the valid views, blend the ORIGINAL colours

