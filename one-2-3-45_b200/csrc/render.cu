@@ -21,7 +21,10 @@ namespace o2345 {
 namespace {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float eluf_(float x) { return x > 0.f ? x : expm1f(x); }
+// Blend-network activations: ex2.approx based (absolute error <= 3e-7 on values of O(1), far below the
+// stated colour tolerance); expm1f/expf cost ~40 / ~15 instructions each and dominated the kernel.
+__device__ __forceinline__ float eluf_(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+__device__ __forceinline__ float fsigmoid_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ int occ_lookup(const float* __restrict__ occ, int D, float px, float py, float pz) {
   float p[3] = {px, py, pz};
@@ -142,7 +145,7 @@ __global__ void ray_mid_kernel(const float* __restrict__ rays_o, const float* __
 // ---------------------------------------------------------------------------------------
 // B11/B12: projector + GeneralRenderingNetwork
 // ---------------------------------------------------------------------------------------
-constexpr int BW = 12;             // warps per CTA
+constexpr int BW = 24;             // warps per CTA
 constexpr int CM = O2345_MAP_CH;   // 60 channels per pixel: rgb(3) + feat(56) + pad(1)
 constexpr int NF = 59;
 
@@ -175,10 +178,9 @@ constexpr int P_S = P_R2B + 4;              // [4]  |s|
 constexpr int P_TOTAL = P_S + 4;
 static_assert(P_TOTAL == O2345_RNET_PACK_FLOATS, "header and kernel disagree on the rendering-net pack");
 
-constexpr int WS_F = 32 * 64;               // per-warp: cached per-view features [32][64]
 constexpr int WS_X = 512;                   // per-warp: two [64][4] activation buffers
 constexpr int WS_RGB = 32 * 4;              // per-warp: rgb of each view
-constexpr int WS_TOTAL = WS_F + WS_X + WS_RGB;
+constexpr int WS_TOTAL = WS_X + WS_RGB;
 constexpr int BLEND_SMEM = (P_TOTAL + BW * WS_TOTAL) * 4;
 
 // y[lane] (and y[lane+32] when OUT > 32) = b + sum_i x[i] * W[i][.]; x in per-warp smem.
@@ -256,6 +258,53 @@ __device__ __forceinline__ void sample_point(const o2345_points& src, int64_t gi
   }
 }
 
+// Features of up to four valid views (slots g0..g0+3 of the `valid` mask): bilinear fetch of the 59 channels
+// (lanes own channels lane and lane+32) plus the direction feature ray_dir_fc(ray_diff) (reference
+// rendering_network.py:44-47,88-90).  Padded slots return zeros and weight 0.  If sRGB != nullptr the original
+// colours of the views are stored at sRGB[slot*4 + c].
+__device__ __forceinline__ void view_group_features(const o2345_views& views, unsigned valid, int g0, int nvalid, float wv,
+                                                    float gx, float gy, float rd0, float rd1, float rd2, float rd3,
+                                                    const float* __restrict__ sP, float* sA4, float* sB4, int lane,
+                                                    int (&vid)[4], float (&wq)[4], float (&a0)[4], float (&a1)[4],
+                                                    float* sRGB) {
+  const int H = views.H, W = views.W;
+  unsigned m = valid;
+  for (int k = 0; k < g0; ++k) m &= m - 1;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    vid[q] = m ? __ffs(m) - 1 : -1;
+    m &= m - 1;
+  }
+  float f0[4], f1[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int vq = vid[q] >= 0 ? vid[q] : 0;
+    wq[q] = vid[q] >= 0 ? __shfl_sync(0xffffffffu, wv, vq) : 0.f;
+    float vgx = __shfl_sync(0xffffffffu, gx, vq), vgy = __shfl_sync(0xffffffffu, gy, vq);
+    fetch_map(views.maps + (int64_t)vq * H * W * CM, H, W, vgx, vgy, lane, f0[q], f1[q]);
+    float r0 = __shfl_sync(0xffffffffu, rd0, vq), r1 = __shfl_sync(0xffffffffu, rd1, vq);
+    float r2 = __shfl_sync(0xffffffffu, rd2, vq), r3 = __shfl_sync(0xffffffffu, rd3, vq);
+    if (lane == 0) sA4[0 * 4 + q] = r0, sA4[1 * 4 + q] = r1, sA4[2 * 4 + q] = r2, sA4[3 * 4 + q] = r3;
+  }
+  __syncwarp();
+  float hd[4], dmy[4], d0[4], d1[4];
+  matvec4<4, 16, 16>(sP + P_D0W, sA4, lane, lane < 16 ? sP[P_D0B + lane] : 0.f, 0.f, hd, dmy);
+  if (lane < 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sB4[lane * 4 + q] = eluf_(hd[q]);
+  }
+  __syncwarp();
+  matvec4<16, 64, 64>(sP + P_D1W, sB4, lane, sP[P_D1B + lane], sP[P_D1B + 32 + lane], d0, d1);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    bool on = g0 + q < nvalid;
+    if (on && sRGB != nullptr && lane < 3) sRGB[(g0 + q) * 4 + lane] = f0[q];
+    a0[q] = on ? f0[q] + eluf_(d0[q]) : 0.f;
+    a1[q] = (on && lane + 32 < NF) ? f1[q] + eluf_(d1[q]) : 0.f;
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(BW * 32, 1)
 render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ active, const float* __restrict__ vol,
                     const float* __restrict__ occ, int D, o2345_views views, int dir_mode,
@@ -266,8 +315,7 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
   for (int i = threadIdx.x; i < P_TOTAL; i += blockDim.x) sP[i] = __ldg(pack + i);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sF = smem + P_TOTAL + warp * WS_TOTAL;
-  float* sX = sF + WS_F;
+  float* sX = smem + P_TOTAL + warp * WS_TOTAL;
   float* sRGB = sX + WS_X;
   const int V = views.V, H = views.H, W = views.W;
   const float abs_s = sP[P_S];
@@ -361,66 +409,32 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
       continue;
     }
 
-    // ---- pass A over the valid views, four at a time: fetch, direction feature, weighted mean
+    // ---- pass A over the valid views, four at a time: fetch, direction feature, weighted mean.
+    //      The features are recomputed in the later passes instead of being cached per warp: the 8 KB
+    //      cache limited the kernel to 12 warps per SM and it was latency bound (ncu: issue active 43 %).
     float mean0 = 0.f, mean1 = 0.f;
     float* sA4 = sX;            // [<=64][4] activations, view-interleaved
     float* sB4 = sX + 256;      // second buffer
     for (int g0 = 0; g0 < nvalid; g0 += 4) {
       int vid[4];
-      float wq[4], f0[4], f1[4];
-      {
-        unsigned m = valid;
-        for (int k = 0; k < g0; ++k) m &= m - 1;
+      float wq[4], a0[4], a1[4];
+      view_group_features(views, valid, g0, nvalid, wv, gx, gy, rd0, rd1, rd2, rd3, sP, sA4, sB4, lane, vid, wq, a0, a1,
+                          sRGB);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          vid[q] = m ? __ffs(m) - 1 : -1;
-          m &= m - 1;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int vq = vid[q] >= 0 ? vid[q] : 0;
-        wq[q] = vid[q] >= 0 ? __shfl_sync(0xffffffffu, wv, vq) : 0.f;
-        float vgx = __shfl_sync(0xffffffffu, gx, vq), vgy = __shfl_sync(0xffffffffu, gy, vq);
-        fetch_map(views.maps + (int64_t)vq * H * W * CM, H, W, vgx, vgy, lane, f0[q], f1[q]);
-        float r0 = __shfl_sync(0xffffffffu, rd0, vq), r1 = __shfl_sync(0xffffffffu, rd1, vq);
-        float r2 = __shfl_sync(0xffffffffu, rd2, vq), r3 = __shfl_sync(0xffffffffu, rd3, vq);
-        if (lane == 0) sA4[0 * 4 + q] = r0, sA4[1 * 4 + q] = r1, sA4[2 * 4 + q] = r2, sA4[3 * 4 + q] = r3;
-      }
-      __syncwarp();
-      // ray_dir_fc: 4 -> 16 -> 59, ELU after both (reference rendering_network.py:44-47,88)
-      float hd[4], dmy[4], d0[4], d1[4];
-      matvec4<4, 16, 16>(sP + P_D0W, sA4, lane, lane < 16 ? sP[P_D0B + lane] : 0.f, 0.f, hd, dmy);
-      if (lane < 16) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sB4[lane * 4 + q] = eluf_(hd[q]);
-      }
-      __syncwarp();
-      matvec4<16, 64, 64>(sP + P_D1W, sB4, lane, sP[P_D1B + lane], sP[P_D1B + 32 + lane], d0, d1);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (g0 + q < nvalid) {
-          if (lane < 3) sRGB[(g0 + q) * 4 + lane] = f0[q];
-          float a0 = f0[q] + eluf_(d0[q]);
-          float a1 = (lane + 32 < NF) ? f1[q] + eluf_(d1[q]) : 0.f;
-          sF[(g0 + q) * 64 + lane] = a0;
-          sF[(g0 + q) * 64 + 32 + lane] = a1;
-          mean0 = fmaf(wq[q], a0, mean0);
-          mean1 = fmaf(wq[q], a1, mean1);
-        }
-      }
-      __syncwarp();
+      for (int q = 0; q < 4; ++q) mean0 = fmaf(wq[q], a0[q], mean0), mean1 = fmaf(wq[q], a1[q], mean1);
     }
-    int slot = 0;
     // ---- pass B: weighted variance around the mean
     float var0 = 0.f, var1 = 0.f;
-    slot = 0;
-    for (unsigned m = valid; m; m &= m - 1, ++slot) {
-      int v = __ffs(m) - 1;
-      float w = __shfl_sync(0xffffffffu, wv, v);
-      float e0 = sF[slot * 64 + lane] - mean0, e1 = sF[slot * 64 + 32 + lane] - mean1;
-      var0 = fmaf(w, e0 * e0, var0);
-      var1 = fmaf(w, e1 * e1, var1);
+    for (int g0 = 0; g0 < nvalid; g0 += 4) {
+      int vid[4];
+      float wq[4], a0[4], a1[4];
+      view_group_features(views, valid, g0, nvalid, wv, gx, gy, rd0, rd1, rd2, rd3, sP, sA4, sB4, lane, vid, wq, a0, a1,
+                          nullptr);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float e0 = a0[q] - mean0, e1 = a1[q] - mean1;
+        var0 = fmaf(wq[q], e0 * e0, var0), var1 = fmaf(wq[q], e1 * e1, var1);
+      }
     }
     // ---- per-sample part of base_fc[0]: [geo(16), mean(59), var(59)] -> 64
     __syncwarp();
@@ -438,24 +452,12 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
     float logit = -3.4e38f;  // lane v keeps the logit of view v
     for (int g0 = 0; g0 < nvalid; g0 += 4) {
       int vid[4];
-      float wq[4];
-      {
-        unsigned m = valid;
-        for (int k = 0; k < g0; ++k) m &= m - 1;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          vid[q] = m ? __ffs(m) - 1 : -1;
-          wq[q] = vid[q] >= 0 ? __shfl_sync(0xffffffffu, wv, vid[q]) : 0.f;
-          m &= m - 1;
-        }
-      }
+      float wq[4], a0[4], a1[4];
+      view_group_features(views, valid, g0, nvalid, wv, gx, gy, rd0, rd1, rd2, rd3, sP, sA4, sB4, lane, vid, wq, a0, a1,
+                          nullptr);
       // base_fc[0], per-view part: x1 = elu(hs + Wf . f_v)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        bool on = g0 + q < nvalid;
-        sA4[lane * 4 + q] = on ? sF[(g0 + q) * 64 + lane] : 0.f;
-        sA4[(lane + 32) * 4 + q] = on ? sF[(g0 + q) * 64 + 32 + lane] : 0.f;
-      }
+      for (int q = 0; q < 4; ++q) sA4[lane * 4 + q] = a0[q], sA4[(lane + 32) * 4 + q] = a1[q];
       __syncwarp();
       float y0[4], y1[4];
       matvec4<NF, 64, 64>(sP + P_B0W + 134 * 64, sA4, lane, hs0, hs1, y0, y1);
@@ -479,7 +481,7 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float visr = eluf_(warp_sum(hv[q] * sP[P_V1V + lane]) + sP[P_V1VB]);
-        vis[q] = sigmoidf_(visr);                       // mask is 1 for the views processed here
+        vis[q] = fsigmoid_(visr);                       // mask is 1 for the views processed here
         x3[q] = x2[q] + eluf_(res[q]);
         sA4[lane * 4 + q] = x3[q] * vis[q];
       }
@@ -489,7 +491,7 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
       matvec4<32, 32, 32>(sP + P_U0W, sA4, lane, sP[P_U0B + lane], 0.f, h2, dmy);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float vis2 = sigmoidf_(warp_sum(eluf_(h2[q]) * sP[P_U1W + lane]) + sP[P_U1B]);
+        float vis2 = fsigmoid_(warp_sum(eluf_(h2[q]) * sP[P_U1W + lane]) + sP[P_U1B]);
         // rgb_fc input [x(32), vis(1), ray_diff(4)]
         sB4[lane * 4 + q] = x3[q];
         int vq = vid[q] >= 0 ? vid[q] : 0;
@@ -524,7 +526,7 @@ render_blend_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ act
     float ex = vmask ? expf(logit - lmax) : 0.f;
     float den = warp_sum(ex);
     float r = 0.f, g = 0.f, b = 0.f;
-    slot = 0;
+    int slot = 0;
     for (unsigned m = valid; m; m &= m - 1, ++slot) {
       int v = __ffs(m) - 1;
       float bw = __shfl_sync(0xffffffffu, ex, v) / den;
