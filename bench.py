@@ -120,13 +120,12 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    tr = build_networks(dev, vol_dim=VOL, states=S.all_states(0) if rank == 0 else S.all_states(0), perturb=0.0)
-    if world > 1:  # the only collective on the path: weights from rank 0 over NVLink
-        for m in (tr.pyramid_feature_network_geometry_lod0, tr.sdf_network_lod0, tr.rendering_network_lod0, tr.variance_network_lod0):
-            for p in list(m.parameters()) + list(m.buffers()):
-                dist.broadcast(p.data, src=0)
+    from o2345 import sharding
+    tr = build_networks(dev, vol_dim=VOL, states=S.all_states(0), perturb=0.0)
+    # the only collective on the path: weights from rank 0 over NVLink (no-op at N = 1)
+    sharding.broadcast_module_weights([tr.pyramid_feature_network_geometry_lod0, tr.sdf_network_lod0,
+                                       tr.rendering_network_lod0, tr.variance_network_lod0], src=0)
     sample, host, host_rays = build_scene(dev, seed=1234 + rank)
-    kw = dict(perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio_lod0=1.0, mode="val")
     tr_val = lambda smp: tr.val_step(smp, perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio_lod0=1.0, chunk_size=CHUNK)
 
     def step_resident():
@@ -167,10 +166,7 @@ def run_gpu(args):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
-    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms = sharding.max_over_ranks([ms, e2e_s * 1e3], dev)
     out = None
     if rank == 0:
         pk = peaks()
