@@ -250,6 +250,52 @@ int o2345_ray_composite(const float* rays_d, int64_t R, int S, const float* mid_
                         float background, float* color_out, float* depth_out, float* weights_out, float* cdf_out,
                         float* alpha_out, float* weights_sum_out, uint8_t* color_mask_out, o2345_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Path A (rows A2-A4, A6): fp16 tensor-core GEMM, tcgen05.mma + TMEM accumulators + TMA operands.
+ * Replaces the cuBLAS / cuDNN calls behind nn.Linear, 1x1 and (im2col'd) 3x3 nn.Conv2d and the
+ * attention einsums of the Zero123 UNet and VAE:
+ *          ldm/modules/diffusionmodules/openaimodel.py:745-777, ldm/modules/attention.py:170-193,
+ *          ldm/modules/diffusionmodules/model.py:535-568.
+ * C[b] = act(alpha * A[b] . B[b]^T + bias) + residual[b];  A [M,K] (row stride lda), B [N,K] (row stride
+ * ldb), fp16, K contiguous; C and residual [M,N] (row stride ldc), C fp16 or fp32.  nh = 0: plain GEMM;
+ * nh > 0: nh * nb independent products, operand z = b * nh + h lives at ptr + h * stride_*_h + b * stride_*_b
+ * (e.g. heads inside a [B, N, H*d] tensor).  act: 0 none, 1 SiLU, 2 GELU.
+ * lda, ldb and the A/B batch strides must be multiples of 8 elements (TMA: 16-byte strides).
+ * ------------------------------------------------------------------------------------------ */
+int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
+                   int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
+                   int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const float* bias, const void* residual,
+                   int act, float alpha, int out_f32, o2345_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Path A glue (rows A1, A3, A4, A6): channel-last fp16 activations [B, H*W, C]; fp32 statistics.
+ * GroupNorm32 / SiLU / conv patch gather: ldm/modules/diffusionmodules/openaimodel.py:92-161,256-276,
+ *   ldm/modules/diffusionmodules/util.py:214-216; LayerNorm / softmax / GEGLU: ldm/modules/attention.py:37-64,
+ *   170-193,214-218; timestep embedding: util.py:151-171; CFG + DDIM update: ldm/models/diffusion/ddim.py:196-243.
+ * ------------------------------------------------------------------------------------------ */
+int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, float* mean, float* rstd,
+                          o2345_stream_t stream);
+/* out [B*Ho*Wo, k*k*C] (column order ky,kx,c) = patches of f(x), f = GroupNorm(+SiLU if act) when mean != NULL.
+ * upsample != 0: nearest x2 replication of x before the convolution.  Zero padding k/2. */
+int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample,
+                          const float* mean, const float* rstd, int G, const float* gamma, const float* beta, int act,
+                          void* out, o2345_stream_t stream);
+int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,
+                         o2345_stream_t stream);
+int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream);
+/* y[M,I] = x[:, :I] * gelu(x[:, I:2I]) */
+int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream);
+int o2345_transpose_tokens(const void* x, int B, int N, int C, void* y, o2345_stream_t stream);
+int o2345_timestep_embedding(const float* t, int B, int dim, void* out, o2345_stream_t stream);
+int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, o2345_stream_t stream);
+int o2345_copy_channels(const void* src, int64_t M, int C, void* dst, int ldd, int off, o2345_stream_t stream);
+int o2345_nchw_f32_to_cl_f16(const float* x, int B, int C, int HW, void* y, int ldy, int off, o2345_stream_t stream);
+int o2345_cl_f16_to_nchw_f32(const void* x, int B, int C, int HW, int ldx, float* y, o2345_stream_t stream);
+/* eps = [unconditional | conditional] halves of n elements each; writes x_prev and (optionally) pred_x0. */
+int o2345_cfg_ddim_update(const float* x, const float* eps, const float* noise, int64_t n, float scale, float a_t,
+                          float a_prev, float sigma_t, float sqrt_one_minus_at, float* x_prev, float* pred_x0,
+                          o2345_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,327 @@
+// fp16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM accumulators), operands fed by TMA.
+// Path A of SURVEY.md section 8 (rows A2-A4, A6): every Linear / 1x1 conv / im2col'd 3x3 conv of the
+// Zero123 UNet and the VAE decoder, and the QK^T / PV products of attention, go through this kernel.
+//
+//   C[M,N] = epilogue( A[M,K] . B[N,K]^T + bias[N] ) (+ residual[M,N])       fp16 in, fp32 accumulate
+//
+// A and B are both K-major (row-major activations [rows, K]; nn.Linear / flattened conv weights [N, K]).
+// One CTA computes a 128 x BN output tile:
+//   warp 0     TMA producer: cp.async.bulk.tensor 128x64 (A) and BNx64 (B) boxes, SWIZZLE_128B, into a
+//              multi-stage shared-memory ring guarded by full/empty mbarriers;
+//   warp 1     allocates TMEM, then one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//              (M=128, N=BN, K=16) four times per stage, committing each stage back to the producer
+//              and the finished accumulator to the epilogue through tcgen05.commit;
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> bias / activation /
+//              residual in registers -> fp16 or fp32 stores (rows past M, columns past N masked;
+//              TMA zero-fills the K, M and N tails on the way in).
+// An optional batch dimension (blockIdx.z) serves the per-head attention products.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace o2345 {
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 28;  // bounded waits: a protocol bug traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4,
+// LBO = 1 (ignored for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1, layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmParams {
+  int M, N, K;
+  int64_t ldc;                 // elements between consecutive rows of C / residual
+  int nh;                      // batched mode: blockIdx.z = b * nh + h
+  int64_t stride_c_h, stride_c_b;  // element offsets of C (and residual) per inner / outer batch index
+  const float* bias;           // [N] or nullptr
+  const __half* residual;      // [M, ldc] or nullptr, added after the activation
+  void* C;
+  int out_f32;                 // 0: fp16 output, 1: fp32 output
+  int act;                     // 0 none, 1 SiLU, 2 GELU(erf)
+  float alpha;                 // scale applied to the accumulator before bias
+  int batched;                 // 4-D tensor maps (K, rows, h, b)
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return x / (1.f + __expf(-x));
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  return x;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, bz = blockIdx.z;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: BN fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      for (int kb = 0; kb < nk; ++kb) {
+        int s = kb % STAGES;
+        uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, A_BYTES + B_BYTES);
+        if (p.batched) {
+          tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * BK, m0, bz % p.nh, bz / p.nh);
+          tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * BK, n0, bz % p.nh, bz / p.nh);
+        } else {
+          tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * BK, m0);
+          tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      for (int kb = 0; kb < nk; ++kb) {
+        int s = kb % STAGES;
+        uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full + s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advancing 16 fp16 along K inside the 128-byte swizzle atom = +32 bytes on the start address
+          umma_f16(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+        }
+        umma_commit(empty + s);   // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);     // accumulator complete
+    }
+  } else {  // ------------------------ epilogue warps 2..5, TMEM lane quarter = warp % 4
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + quarter * 32 + lane;
+    const int64_t crow = (p.batched ? (int64_t)(bz % p.nh) * p.stride_c_h + (int64_t)(bz / p.nh) * p.stride_c_b : 0) +
+                         (int64_t)row * p.ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
+      if (row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          int col = n0 + c0 + j;
+          if (col >= p.N) break;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x = __uint_as_float(r[j + e]) * p.alpha;
+            if (p.bias && col + e < p.N) x += __ldg(p.bias + col + e);
+            v[e] = apply_act(x, p.act);
+          }
+          if (col + 8 <= p.N && (p.ldc & 7) == 0) {
+            if (p.residual) {
+              uint4 q = *reinterpret_cast<const uint4*>(p.residual + crow + col);
+              const __half* h = reinterpret_cast<const __half*>(&q);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += __half2float(h[e]);
+            }
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.C) + crow + col;
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              __half2 h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + crow + col) = *reinterpret_cast<uint4*>(h);
+            }
+          } else {
+            for (int e = 0; e < 8 && col + e < p.N; ++e) {
+              float x = v[e];
+              if (p.residual) x += __half2float(p.residual[crow + col + e]);
+              if (p.out_f32) reinterpret_cast<float*>(p.C)[crow + col + e] = x;
+              else reinterpret_cast<__half*>(p.C)[crow + col + e] = __float2half_rn(x);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [nb, nh, rows, K] fp16 view with row stride ld and batch strides sh / sb (elements); box = 64 x box_rows (x 1 x 1)
+int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t ld, int nh, int nb, int64_t sh, int64_t sb,
+             int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return O2345_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(nh > 0 ? nh : 1), (cuuint64_t)(nb > 0 ? nb : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  int rank = nh > 0 ? 4 : 2;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld K=%lld ld=%lld)", (int)r, (long long)rows, (long long)K, (long long)ld); return O2345_ECUDA; }
+  return O2345_OK;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    O2345_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr = true;
+  }
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), batch > 0 ? batch : 1);
+  gemm_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SMEM, st>>>(a, b, p);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+}  // namespace
+}  // namespace o2345
+
+using namespace o2345;
+
+extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
+                              int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
+                              int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const float* bias,
+                              const void* residual, int act, float alpha, int out_f32, o2345_stream_t stream) {
+  O2345_CHECK_ARG(A && B && C, "null pointer");
+  O2345_CHECK_ARG(M > 0 && N > 0 && K > 0 && nh >= 0 && (nh == 0 || nb >= 1), "bad sizes");
+  O2345_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "row strides of A and B must be multiples of 8 fp16 (16 bytes) for TMA");
+  O2345_CHECK_ARG(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, "A and B must be 16-byte aligned");
+  O2345_CHECK_ARG(nh == 0 || ((stride_a_h % 8) == 0 && (stride_a_b % 8) == 0 && (stride_b_h % 8) == 0 && (stride_b_b % 8) == 0),
+                  "batch strides must be multiples of 8 fp16");
+  O2345_CHECK_ARG(act >= 0 && act <= 2, "unknown activation");
+  CUtensorMap ma, mb;
+  const int BN = N <= 64 ? 64 : 128;
+  int rc = make_map(&ma, A, M, K, lda, nh, nb, stride_a_h, stride_a_b, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, B, N, K, ldb, nh, nb, stride_b_h, stride_b_b, BN);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K, p.ldc = ldc, p.nh = nh > 0 ? nh : 1, p.stride_c_h = stride_c_h, p.stride_c_b = stride_c_b;
+  p.bias = bias, p.residual = reinterpret_cast<const __half*>(residual), p.C = C, p.out_f32 = out_f32, p.act = act;
+  p.alpha = alpha, p.batched = nh > 0 ? 1 : 0;
+  int batch = nh > 0 ? nh * nb : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 64) return launch<64, 6>(ma, mb, p, batch, st);
+  return launch<128, 5>(ma, mb, p, batch, st);
+}

@@ -1,0 +1,318 @@
+// Path A glue kernels around the tcgen05 GEMM: everything in the Zero123 UNet / VAE that is not a matrix
+// product.  Activations are channel-last fp16 ([B, H*W, C]); normalisation statistics, softmax and the
+// DDIM update are computed in fp32, matching the reference's autocast policy (GroupNorm32 / LayerNorm /
+// softmax in fp32: ldm/modules/diffusionmodules/util.py:214-216, SURVEY.md section 8 header).
+//
+//   groupnorm_stats      per (batch, group) mean / rstd                     openaimodel.py:256-276 (GroupNorm32)
+//   norm_act_im2col      GroupNorm apply (+SiLU) fused with the 3x3 / 1x1 patch gather (optionally behind a
+//                        nearest x2 up-sampling or with stride 2) -> the K-major A operand of the conv GEMM
+//   layernorm_rows       attention.py:214-218
+//   softmax_rows         attention.py:189 (fp16 scores in, fp32 math, fp16 probabilities out)
+//   geglu                attention.py:37-45
+//   transpose_tokens     [B,N,C] -> [B,C,N] for the PV product
+//   timestep_embedding   util.py:151-171
+//   cfg_ddim_update      ddim.py:212-243 (classifier-free guidance + x0 / direction / noise update)
+//   layout converters    NCHW fp32 <-> channel-last fp16, channel concat
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace o2345 {
+namespace {
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+// one CTA per (batch, group): x [B, HW, C] fp16, G groups of C/G channels
+__global__ void groupnorm_stats_kernel(const __half* __restrict__ x, int HW, int C, int G, float eps,
+                                       float* __restrict__ mean, float* __restrict__ rstd) {
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int cg = C / G;
+  const __half* base = x + (int64_t)b * HW * C + g * cg;
+  float s = 0.f, q = 0.f;
+  for (int i = threadIdx.x; i < HW * cg; i += blockDim.x) {
+    int p = i / cg, c = i - p * cg;
+    float v = __half2float(base[(int64_t)p * C + c]);
+    s += v, q = fmaf(v, v, q);
+  }
+  __shared__ float ss[32], sq[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = s, sq[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int nw = blockDim.x >> 5;
+    s = threadIdx.x < nw ? ss[threadIdx.x] : 0.f, q = threadIdx.x < nw ? sq[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (threadIdx.x == 0) {
+      float n = (float)HW * cg, m = s / n;
+      float var = fmaxf(q / n - m * m, 0.f);
+      mean[blockIdx.x] = m, rstd[blockIdx.x] = rsqrtf(var + eps);
+    }
+  }
+}
+
+// out[(b, oy, ox), (ky, kx, c)] = f(in[b, iy, ix, c]);  f = optional GroupNorm(+SiLU).  KS in {1,3}; `up` doubles the
+// input grid by nearest-neighbour replication before the convolution; zero padding of KS/2.
+__global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int KS, int stride, int up,
+                                       const float* __restrict__ mean, const float* __restrict__ rstd, int G,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                       __half* __restrict__ out, int Ho, int Wo) {
+  const int c8 = C >> 3;  // 8 channels (16 bytes) per thread
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)B * Ho * Wo * KS * KS * c8;
+  if (idx >= total) return;
+  int cc = (int)(idx % c8);
+  int kk = (int)((idx / c8) % (KS * KS));
+  int64_t pix = idx / ((int64_t)c8 * KS * KS);
+  int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
+  int ky = kk / KS, kx = kk % KS, pad = KS / 2;
+  int Hin = up ? 2 * H : H, Win = up ? 2 * W : W;
+  int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
+    int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
+    uint4 v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + sy) * W + sx) * C + cc * 8);
+    if (mean) {
+      const __half* h = reinterpret_cast<const __half*>(&v);
+      __half r[8];
+      int cg = C / G;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int c = cc * 8 + e, g = c / cg;
+        float f = (__half2float(h[e]) - mean[b * G + g]) * rstd[b * G + g] * gamma[c] + beta[c];
+        if (act) f = silu(f);
+        r[e] = __float2half_rn(f);
+      }
+      o = *reinterpret_cast<uint4*>(r);
+    } else {
+      o = v;
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (pix * KS * KS + kk) * C + cc * 8) = o;
+}
+
+// one warp per row: y = (x - mean) * rstd * gamma + beta, fp32 math
+__global__ void layernorm_rows_kernel(const __half* __restrict__ x, int64_t M, int C, float eps,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      __half* __restrict__ y) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const __half* xr = x + row * C;
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < C; c += 32) { float v = __half2float(xr[c]); s += v, q = fmaf(v, v, q); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
+  float m = s / C, r = rsqrtf(fmaxf(q / C - m * m, 0.f) + eps);
+  for (int c = lane; c < C; c += 32) y[row * C + c] = __float2half_rn((__half2float(xr[c]) - m) * r * gamma[c] + beta[c]);
+}
+
+// one warp per row of length n (<= 1024): probabilities in fp16
+__global__ void softmax_rows_kernel(const __half* __restrict__ s, int64_t rows, int n, __half* __restrict__ p) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __half* sr = s + row * n;
+  float v[32];
+  float mx = -3.4e38f;
+  int cnt = (n + 31) / 32;
+  for (int i = 0; i < cnt; ++i) {
+    int c = lane + 32 * i;
+    v[i] = c < n ? __half2float(sr[c]) : -3.4e38f;
+    mx = fmaxf(mx, v[i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = 0; i < cnt; ++i) { v[i] = (lane + 32 * i < n) ? expf(v[i] - mx) : 0.f; sum += v[i]; }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  float inv = 1.f / sum;
+  for (int i = 0; i < cnt; ++i) { int c = lane + 32 * i; if (c < n) p[row * n + c] = __float2half_rn(v[i] * inv); }
+}
+
+__global__ void geglu_kernel(const __half* __restrict__ x, int64_t M, int I, __half* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * I) return;
+  int64_t r = i / I;
+  int c = (int)(i - r * I);
+  float a = __half2float(x[r * 2 * I + c]), g = __half2float(x[r * 2 * I + I + c]);
+  y[i] = __float2half_rn(a * (0.5f * g * (1.f + erff(g * 0.70710678118654752f))));
+}
+
+// [B, N, C] -> [B, C, N]
+__global__ void transpose_tokens_kernel(const __half* __restrict__ x, int N, int C, __half* __restrict__ y) {
+  __shared__ __half tile[32][33];
+  int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int n = n0 + j, c = c0 + threadIdx.x;
+    if (n < N && c < C) tile[j][threadIdx.x] = x[((int64_t)b * N + n) * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, n = n0 + threadIdx.x;
+    if (n < N && c < C) y[((int64_t)b * C + c) * N + n] = tile[threadIdx.x][j];
+  }
+}
+
+// timestep_embedding(t, dim): [cos(t * f_i) | sin(t * f_i)], f_i = exp(-ln(10000) * i / half)   (util.py:151-171)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int half_dim = dim / 2;
+  if (i >= B * half_dim) return;
+  int b = i / half_dim, k = i % half_dim;
+  float f = expf(-logf(10000.f) * (float)k / (float)half_dim);
+  float a = t[b] * f;
+  out[b * dim + k] = __float2half_rn(cosf(a));
+  out[b * dim + half_dim + k] = __float2half_rn(sinf(a));
+}
+
+// y[b, p, c] += e[b, c]   (ResBlock: h + emb_out[..., None, None], openaimodel.py:271)
+__global__ void add_channel_bias_kernel(__half* __restrict__ y, const __half* __restrict__ e, int HW, int C, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int c = (int)(i % C);
+  int64_t b = i / ((int64_t)HW * C);
+  y[i] = __float2half_rn(__half2float(y[i]) + __half2float(e[b * C + c]));
+}
+
+// dst[:, off:off+C] = src  (channel concat on channel-last rows)
+__global__ void copy_channels_kernel(const __half* __restrict__ src, int64_t M, int C, __half* __restrict__ dst, int ldd, int off) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int c8 = C >> 3;
+  if (i >= M * c8) return;
+  int64_t r = i / c8;
+  int c = (int)(i - r * c8) * 8;
+  *reinterpret_cast<uint4*>(dst + r * ldd + off + c) = *reinterpret_cast<const uint4*>(src + r * C + c);
+}
+
+__global__ void nchw_f32_to_cl_f16_kernel(const float* __restrict__ x, int B, int C, int HW, __half* __restrict__ y, int ldy, int off) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * C * HW) return;
+  int p = (int)(i % HW), c = (int)((i / HW) % C);
+  int64_t b = i / ((int64_t)HW * C);
+  y[(b * HW + p) * ldy + off + c] = __float2half_rn(x[i]);
+}
+
+__global__ void cl_f16_to_nchw_f32_kernel(const __half* __restrict__ x, int B, int C, int HW, int ldx, float* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * C * HW) return;
+  int p = (int)(i % HW), c = (int)((i / HW) % C);
+  int64_t b = i / ((int64_t)HW * C);
+  y[i] = __half2float(x[(b * HW + p) * ldx + c]);
+}
+
+// e_t = e_uc + s (e_c - e_uc); pred_x0 = (x - sqrt(1-a) e_t)/sqrt(a); x_prev = sqrt(a') pred_x0 + sqrt(1-a'-sigma^2) e_t
+// + sigma * noise.  eps holds [uncond batch | cond batch] (ddim.py:196-243); all fp32.
+__global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                                       int64_t n, float scale, float a_t, float a_prev, float sigma_t, float sqrt_1m_at,
+                                       float* __restrict__ x_prev, float* __restrict__ pred_x0) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float eu = eps[i], ec = eps[n + i];
+  float e = eu + scale * (ec - eu);
+  float p0 = (x[i] - sqrt_1m_at * e) / sqrtf(a_t);
+  float dir = sqrtf(1.f - a_prev - sigma_t * sigma_t) * e;
+  float nz = sigma_t * (noise ? noise[i] : 0.f);
+  x_prev[i] = sqrtf(a_prev) * p0 + dir + nz;
+  if (pred_x0) pred_x0[i] = p0;
+}
+
+}  // namespace
+}  // namespace o2345
+
+using namespace o2345;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, float* mean, float* rstd,
+                                     o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && mean && rstd && C % G == 0, "bad arguments");
+  groupnorm_stats_kernel<<<B * G, 256, 0, ST>>>((const __half*)x, HW, C, G, eps, mean, rstd);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample,
+                                     const float* mean, const float* rstd, int G, const float* gamma, const float* beta,
+                                     int act, void* out, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && out && (C % 8) == 0 && (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "bad arguments");
+  O2345_CHECK_ARG(!mean || (rstd && gamma && beta && G > 0 && C % G == 0), "incomplete GroupNorm arguments");
+  int Hin = upsample ? 2 * H : H, Win = upsample ? 2 * W : W;
+  int pad = ksize / 2;
+  int Ho = (Hin + 2 * pad - ksize) / stride + 1, Wo = (Win + 2 * pad - ksize) / stride + 1;
+  int64_t total = (int64_t)B * Ho * Wo * ksize * ksize * (C / 8);
+  norm_act_im2col_kernel<<<cdiv(total, 256), 256, 0, ST>>>((const __half*)x, B, H, W, C, ksize, stride, upsample, mean, rstd, G,
+                                                           gamma, beta, act, (__half*)out, Ho, Wo);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,
+                                    o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && y && gamma && beta, "null pointer");
+  layernorm_rows_kernel<<<cdiv(M, 8), 256, 0, ST>>>((const __half*)x, M, C, eps, gamma, beta, (__half*)y);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream) {
+  O2345_CHECK_ARG(s && p && n >= 1 && n <= 1024, "row length must be 1..1024");
+  softmax_rows_kernel<<<cdiv(rows, 8), 256, 0, ST>>>((const __half*)s, rows, n, (__half*)p);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && y, "null pointer");
+  geglu_kernel<<<cdiv(M * I, 256), 256, 0, ST>>>((const __half*)x, M, I, (__half*)y);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_transpose_tokens(const void* x, int B, int N, int C, void* y, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && y, "null pointer");
+  transpose_tokens_kernel<<<dim3(cdiv(N, 32), cdiv(C, 32), B), dim3(32, 8), 0, ST>>>((const __half*)x, N, C, (__half*)y);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_timestep_embedding(const float* t, int B, int dim, void* out, o2345_stream_t stream) {
+  O2345_CHECK_ARG(t && out && dim % 2 == 0, "bad arguments");
+  timestep_embedding_kernel<<<cdiv(B * dim / 2, 128), 128, 0, ST>>>(t, B, dim, (__half*)out);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, o2345_stream_t stream) {
+  O2345_CHECK_ARG(y && e, "null pointer");
+  int64_t total = (int64_t)B * HW * C;
+  add_channel_bias_kernel<<<cdiv(total, 256), 256, 0, ST>>>((__half*)y, (const __half*)e, HW, C, total);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_copy_channels(const void* src, int64_t M, int C, void* dst, int ldd, int off, o2345_stream_t stream) {
+  O2345_CHECK_ARG(src && dst && (C % 8) == 0 && (ldd % 8) == 0 && (off % 8) == 0, "channels must be multiples of 8");
+  copy_channels_kernel<<<cdiv(M * (C / 8), 256), 256, 0, ST>>>((const __half*)src, M, C, (__half*)dst, ldd, off);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_nchw_f32_to_cl_f16(const float* x, int B, int C, int HW, void* y, int ldy, int off, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && y, "null pointer");
+  nchw_f32_to_cl_f16_kernel<<<cdiv((int64_t)B * C * HW, 256), 256, 0, ST>>>(x, B, C, HW, (__half*)y, ldy, off);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_cl_f16_to_nchw_f32(const void* x, int B, int C, int HW, int ldx, float* y, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && y, "null pointer");
+  cl_f16_to_nchw_f32_kernel<<<cdiv((int64_t)B * C * HW, 256), 256, 0, ST>>>((const __half*)x, B, C, HW, ldx, y);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_cfg_ddim_update(const float* x, const float* eps, const float* noise, int64_t n, float scale, float a_t,
+                                     float a_prev, float sigma_t, float sqrt_one_minus_at, float* x_prev, float* pred_x0,
+                                     o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && eps && x_prev, "null pointer");
+  cfg_ddim_update_kernel<<<cdiv(n, 256), 256, 0, ST>>>(x, eps, noise, n, scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, x_prev, pred_x0);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}

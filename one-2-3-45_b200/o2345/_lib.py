@@ -71,6 +71,22 @@ _SIGS = {
                                       c_fp, c_fp]),
     "o2345_render_blend": (C.c_int, [C.POINTER(Points), c_i64, c_fp, c_fp, c_fp, C.c_int, C.POINTER(Views),
                                      C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_gemm_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int,
+                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_fp, c_fp, C.c_int, C.c_float, C.c_int, c_fp]),
+    "o2345_groupnorm_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp]),
+    "o2345_norm_act_im2col": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp,
+                                        C.c_int, c_fp, c_fp, C.c_int, c_fp, c_fp]),
+    "o2345_layernorm_rows": (C.c_int, [c_fp, c_i64, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp]),
+    "o2345_softmax_rows": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
+    "o2345_geglu": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
+    "o2345_transpose_tokens": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
+    "o2345_timestep_embedding": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp]),
+    "o2345_add_channel_bias": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp]),
+    "o2345_copy_channels": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, C.c_int, C.c_int, c_fp]),
+    "o2345_nchw_f32_to_cl_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, C.c_int, c_fp]),
+    "o2345_cl_f16_to_nchw_f32": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
+    "o2345_cfg_ddim_update": (C.c_int, [c_fp, c_fp, c_fp, c_i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        c_fp, c_fp, c_fp]),
     "o2345_ray_composite": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float,
                                       C.c_float, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
 }
