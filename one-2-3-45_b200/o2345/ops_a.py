@@ -11,29 +11,115 @@ from .ops import _p, _stream
 _f16, _f32 = torch.float16, torch.float32
 
 
+def _v(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
 def gemm(a, b, bias=None, residual=None, act=0, alpha=1.0, out_dtype=_f16, out=None):
     """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + residual.  a, b fp16 with contiguous K; rows may be strided."""
     assert a.dtype == _f16 and b.dtype == _f16 and a.stride(-1) == 1 and b.stride(-1) == 1
     M, K = a.shape
     N = b.shape[0]
-    assert b.shape[1] == K
+    assert b.shape[1] == K, (a.shape, b.shape)
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     assert out.stride(-1) == 1
-    L.call("o2345_gemm_f16", C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), M, N, K,
-           a.stride(0), b.stride(0), out.stride(0), 0, 0, 0, 0, _p(bias, _f32),
-           None if residual is None else C.c_void_p(residual.data_ptr()), int(act), float(alpha),
-           int(out.dtype == _f32), _stream())
+    if residual is not None:
+        assert residual.dtype == _f16 and residual.stride(0) == out.stride(0) and residual.stride(-1) == 1
+    L.call("o2345_gemm_f16", _v(a), _v(b), _v(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), 0, 0, 0, 0, 0, 0, 0, 0,
+           _p(bias, _f32), _v(residual), int(act), float(alpha), int(out.dtype == _f32), _stream())
     return out
 
 
-def bgemm(a, b, alpha=1.0, out_dtype=_f16):
-    """Batched: out[B,M,N] = alpha * a[B,M,K] @ b[B,N,K]^T (attention scores / PV)."""
-    assert a.dtype == _f16 and b.dtype == _f16 and a.stride(-1) == 1 and b.stride(-1) == 1
-    Bn, M, K = a.shape
-    N = b.shape[1]
-    out = torch.empty(Bn, M, N, dtype=out_dtype, device=a.device)
-    L.call("o2345_gemm_f16", C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()), M, N, K,
-           a.stride(1), b.stride(1), out.stride(1), Bn, a.stride(0), b.stride(0), out.stride(0), None, None, 0,
-           float(alpha), int(out_dtype == _f32), _stream())
+def bgemm(a, b, out, nh, nb, sa, sb, sc, M, N, K, lda, ldb, ldc, alpha=1.0):
+    """nh*nb products; sa/sb/sc = (stride_h, stride_b) element offsets of the operand for batch z = b*nh + h."""
+    L.call("o2345_gemm_f16", _v(a), _v(b), _v(out), M, N, K, lda, ldb, ldc, nh, nb, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1],
+           None, None, 0, float(alpha), int(out.dtype == _f32), _stream())
     return out
+
+
+def groupnorm_stats(x, B, HW, C, G=32, eps=1e-5):
+    mean = torch.empty(B * G, dtype=_f32, device=x.device)
+    rstd = torch.empty_like(mean)
+    L.call("o2345_groupnorm_stats", _v(x), B, HW, C, G, float(eps), _v(mean), _v(rstd), _stream())
+    return mean, rstd
+
+
+def norm_act_im2col(x, B, H, W, C, ksize=3, stride=1, upsample=False, gn=None, act=False):
+    """gn = (mean, rstd, G, gamma, beta) or None.  Returns ([B*Ho*Wo, k*k*C] fp16, Ho, Wo)."""
+    Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
+    pad = ksize // 2
+    Ho, Wo = (Hin + 2 * pad - ksize) // stride + 1, (Win + 2 * pad - ksize) // stride + 1
+    out = torch.empty(B * Ho * Wo, ksize * ksize * C, dtype=_f16, device=x.device)
+    mean, rstd, G, gamma, beta = gn if gn is not None else (None, None, 0, None, None)
+    L.call("o2345_norm_act_im2col", _v(x), B, H, W, C, ksize, stride, int(upsample), _v(mean), _v(rstd), G, _v(gamma), _v(beta),
+           int(act), _v(out), _stream())
+    return out, Ho, Wo
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    M, Cc = x.shape
+    y = torch.empty_like(x)
+    L.call("o2345_layernorm_rows", _v(x), M, Cc, float(eps), _v(gamma), _v(beta), _v(y), _stream())
+    return y
+
+
+def softmax_rows(s):
+    rows, n = s.numel() // s.shape[-1], s.shape[-1]
+    p = torch.empty_like(s)
+    L.call("o2345_softmax_rows", _v(s), rows, n, _v(p), _stream())
+    return p
+
+
+def geglu(x):
+    M, I2 = x.shape
+    y = torch.empty(M, I2 // 2, dtype=_f16, device=x.device)
+    L.call("o2345_geglu", _v(x), M, I2 // 2, _v(y), _stream())
+    return y
+
+
+def transpose_tokens(x, B, N, Cc):
+    y = torch.empty(B, Cc, N, dtype=_f16, device=x.device)
+    L.call("o2345_transpose_tokens", _v(x), B, N, Cc, _v(y), _stream())
+    return y
+
+
+def timestep_embedding(t, dim):
+    t = t.to(_f32).contiguous()
+    out = torch.empty(t.shape[0], dim, dtype=_f16, device=t.device)
+    L.call("o2345_timestep_embedding", _v(t), t.shape[0], dim, _v(out), _stream())
+    return out
+
+
+def add_channel_bias(y, e, B, HW, Cc):
+    L.call("o2345_add_channel_bias", _v(y), _v(e), B, HW, Cc, _stream())
+    return y
+
+
+def copy_channels(src, dst, off):
+    M, Cc = src.shape
+    L.call("o2345_copy_channels", _v(src), M, Cc, _v(dst), dst.stride(0), off, _stream())
+
+
+def nchw_to_cl(x, out=None, off=0):
+    B, Cc, H, W = x.shape
+    x = x.to(_f32).contiguous()
+    if out is None:
+        out = torch.zeros(B * H * W, Cc, dtype=_f16, device=x.device)
+    L.call("o2345_nchw_f32_to_cl_f16", _v(x), B, Cc, H * W, _v(out), out.stride(0), off, _stream())
+    return out
+
+
+def cl_to_nchw(x, B, Cc, H, W):
+    y = torch.empty(B, Cc, H, W, dtype=_f32, device=x.device)
+    L.call("o2345_cl_f16_to_nchw_f32", _v(x), B, Cc, H * W, x.stride(0), _v(y), _stream())
+    return y
+
+
+def cfg_ddim_update(x, eps2, noise, scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, want_x0=True):
+    n = x.numel()
+    x_prev = torch.empty_like(x)
+    pred = torch.empty_like(x) if want_x0 else None
+    L.call("o2345_cfg_ddim_update", _v(x), _v(eps2), _v(noise), n, float(scale), float(a_t), float(a_prev), float(sigma_t),
+           float(sqrt_one_minus_at), _v(x_prev), _v(pred), _stream())
+    return x_prev, pred

@@ -51,11 +51,23 @@ def test_gemm_epilogues_and_fp16_out():
     assert (out - ref(q, b[:, :64])).abs().max().item() < 1e-2
 
 
-def test_batched_gemm():
+def test_batched_gemm_heads_inside_a_token_tensor():
+    """q, k live as column blocks of a [B, N, 3*H*d] tensor (fused qkv projection); scores per (b, h)."""
     from o2345 import ops_a
     g = torch.Generator(device="cuda").manual_seed(2)
-    a = (torch.randn(16, 256, 40, device="cuda", generator=g) * 0.5).half()
-    b = (torch.randn(16, 256, 40, device="cuda", generator=g) * 0.5).half()
-    out = ops_a.bgemm(a, b, alpha=40 ** -0.5, out_dtype=torch.float32)
-    want = torch.einsum("bik,bjk->bij", a.float(), b.float()) * 40 ** -0.5
-    assert (out - want).abs().max().item() < 5e-3
+    B, N, H, d = 2, 256, 8, 40
+    Cc = H * d
+    qkv = (torch.randn(B, N, 3 * Cc, device="cuda", generator=g) * 0.5).half()
+    q, k = qkv[:, :, :Cc], qkv[:, :, Cc:2 * Cc]
+    out = torch.empty(B * H, N, N, dtype=torch.float16, device="cuda")
+    ops_a.bgemm(q, k, out, H, B, (d, N * 3 * Cc), (d, N * 3 * Cc), (N * N, H * N * N), N, N, d, 3 * Cc, 3 * Cc, N, alpha=d ** -0.5)
+    want = torch.einsum("bihd,bjhd->bhij", q.float().view(B, N, H, d), k.float().view(B, N, H, d)) * d ** -0.5
+    assert (out.float().view(B, H, N, N) - want).abs().max().item() < 2e-2
+    # P @ V with V^T [B, C, N] and the result written back into [B, N, C]
+    p = torch.softmax(want, -1).half().contiguous().view(B * H, N, N)
+    v = qkv[:, :, 2 * Cc:]
+    vt = ops_a.transpose_tokens(v.contiguous(), B, N, Cc)
+    o = torch.zeros(B, N, Cc, dtype=torch.float16, device="cuda")
+    ops_a.bgemm(p, vt, o, H, B, (N * N, H * N * N), (d * N, Cc * N), (d, N * Cc), N, d, N, N, N, Cc)
+    want_o = torch.einsum("bhij,bjhd->bihd", p.float().view(B, H, N, N), v.float().view(B, N, H, d)).reshape(B, N, Cc)
+    assert (o.float() - want_o).abs().max().item() < 2e-2
