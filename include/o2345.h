@@ -285,6 +285,7 @@ int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float
 int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream);
 /* y[M,I] = x[:, :I] * gelu(x[:, I:2I]) */
 int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream);
+int o2345_silu(const void* x, int64_t n, void* y, o2345_stream_t stream);
 int o2345_transpose_tokens(const void* x, int B, int N, int C, void* y, o2345_stream_t stream);
 int o2345_timestep_embedding(const float* t, int B, int dim, void* out, o2345_stream_t stream);
 int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, o2345_stream_t stream);

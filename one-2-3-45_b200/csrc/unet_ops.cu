@@ -136,6 +136,11 @@ __global__ void geglu_kernel(const __half* __restrict__ x, int64_t M, int I, __h
   y[i] = __float2half_rn(a * (0.5f * g * (1.f + erff(g * 0.70710678118654752f))));
 }
 
+__global__ void silu_kernel(const __half* __restrict__ x, int64_t n, __half* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2half_rn(silu(__half2float(x[i])));
+}
+
 // [B, N, C] -> [B, C, N]
 __global__ void transpose_tokens_kernel(const __half* __restrict__ x, int N, int C, __half* __restrict__ y) {
   __shared__ __half tile[32][33];
@@ -261,6 +266,13 @@ extern "C" int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o
 extern "C" int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y, "null pointer");
   geglu_kernel<<<cdiv(M * I, 256), 256, 0, ST>>>((const __half*)x, M, I, (__half*)y);
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_silu(const void* x, int64_t n, void* y, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && y, "null pointer");
+  silu_kernel<<<cdiv(n, 256), 256, 0, ST>>>((const __half*)x, n, (__half*)y);
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -79,6 +79,7 @@ _SIGS = {
     "o2345_layernorm_rows": (C.c_int, [c_fp, c_i64, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp]),
     "o2345_softmax_rows": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
     "o2345_geglu": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
+    "o2345_silu": (C.c_int, [c_fp, c_i64, c_fp, c_fp]),
     "o2345_transpose_tokens": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "o2345_timestep_embedding": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp]),
     "o2345_add_channel_bias": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp]),

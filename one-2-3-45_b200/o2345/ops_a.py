@@ -123,3 +123,9 @@ def cfg_ddim_update(x, eps2, noise, scale, a_t, a_prev, sigma_t, sqrt_one_minus_
     L.call("o2345_cfg_ddim_update", _v(x), _v(eps2), _v(noise), n, float(scale), float(a_t), float(a_prev), float(sigma_t),
            float(sqrt_one_minus_at), _v(x_prev), _v(pred), _stream())
     return x_prev, pred
+
+
+def silu(x):
+    y = torch.empty_like(x)
+    L.call("o2345_silu", _v(x), x.numel(), _v(y), _stream())
+    return y

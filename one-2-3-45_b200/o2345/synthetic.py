@@ -298,3 +298,29 @@ def images(n_views=32, H=256, W=256, seed=1234):
             tex = 0.5 + 0.4 * np.sin(fr[c] * xs + ph[c]) * np.cos(fr[(c + 1) % 3] * ys - ph[c])
             out[v, c][inside] = tex[inside]
     return (np.round(out * 255.0) / 255.0).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# path A: seeded Zero123 UNet weights (860 M parameters, generated on the fly -- never stored)
+# --------------------------------------------------------------------------------------
+
+def unet_state(seed=0, gain=0.7):
+    """State dict of the Zero123 UNet (reference keys / shapes, openaimodel.py:414-735): weights
+    N(0, gain / sqrt(fan_in)), small biases, norm scales around 1.  The reference zero-initialises several
+    output convolutions (`zero_module`); they get the same random treatment here so that every layer matters."""
+    import torch
+    from .unet import UNetModel
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in UNetModel().state_dict().items()}
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        if len(shp) >= 2:
+            fan_in = int(np.prod(shp[1:]))
+            sd[k] = (rng.standard_normal(shp, dtype=np.float32) * np.float32(gain / math.sqrt(fan_in)))
+        elif ".norm" in k or "in_layers.0" in k or "out_layers.0" in k or k.startswith("out.0"):
+            sd[k] = (1.0 + 0.1 * rng.standard_normal(shp, dtype=np.float32)) if k.endswith("weight") else \
+                (0.05 * rng.standard_normal(shp, dtype=np.float32))
+        else:
+            sd[k] = 0.02 * rng.standard_normal(shp, dtype=np.float32)
+    return sd

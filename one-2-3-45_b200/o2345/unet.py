@@ -1,0 +1,305 @@
+"""Zero123 UNetModel on the o2345 tensor-core path.
+
+Mirror of reference ldm/modules/diffusionmodules/openaimodel.py:414-777 for the configuration that
+configs/sd-objaverse-finetune-c_concat-256.yaml:28-43 instantiates (spatial transformers, depth 1,
+legacy=False): the module tree below reproduces the reference's state-dict keys
+(`input_blocks.{i}.{j}.in_layers.0.weight`, `...transformer_blocks.0.attn1.to_q.weight`, ...), so a
+`model.diffusion_model.*` checkpoint loads directly; `forward(x, timesteps, context)` has the reference
+signature and returns the epsilon prediction [N,4,H,W] in fp32 (values rounded through fp16 exactly where
+autocast would round them).
+
+Execution: activations are channel-last fp16 [N*H*W, C].  Every Linear / 1x1 conv / 3x3 conv is one
+tcgen05 GEMM (csrc/gemm_tc.cu); 3x3 convs gather their patches with GroupNorm+SiLU fused into the
+gather (csrc/unet_ops.cu); self-attention is QK^T -> fp32 softmax -> PV with per-head batched GEMMs.
+Cross-attention: Zero123 conditions on ONE token, so softmax over a single key is exactly 1 and
+attn2(x) = to_out(to_v(context)) broadcast over the image -- computed as two
+[N,C] GEMMs instead of N*H*W-row attention; contexts with more than one token use the general path.
+`use_checkpoint` is accepted and ignored (inference).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops_a as A
+
+_f16, _f32 = torch.float16, torch.float32
+
+
+# ----------------------------------------------------------------------------- parameter holders
+def _gn(c, eps=1e-5):
+    return nn.GroupNorm(32, c, eps=eps)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, ch, emb_ch, out_ch):
+        super().__init__()
+        self.channels, self.out_channels = ch, out_ch
+        self.in_layers = nn.Sequential(_gn(ch), nn.SiLU(), nn.Conv2d(ch, out_ch, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_ch, out_ch))
+        self.out_layers = nn.Sequential(_gn(out_ch), nn.SiLU(), nn.Dropout(0.0), nn.Conv2d(out_ch, out_ch, 3, padding=1))
+        self.skip_connection = nn.Identity() if ch == out_ch else nn.Conv2d(ch, out_ch, 1)
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, query_dim, context_dim, heads, dim_head):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.dim_head = heads, dim_head
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(context_dim or query_dim, inner, bias=False)
+        self.to_v = nn.Linear(context_dim or query_dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(0.0))
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.Sequential(GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim))
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, dim_head, context_dim):
+        super().__init__()
+        self.attn1 = CrossAttention(dim, None, heads, dim_head)
+        self.ff = FeedForward(dim)
+        self.attn2 = CrossAttention(dim, context_dim, heads, dim_head)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+
+
+class SpatialTransformer(nn.Module):
+    def __init__(self, ch, heads, dim_head, context_dim):
+        super().__init__()
+        inner = heads * dim_head
+        self.norm = _gn(ch, eps=1e-6)
+        self.proj_in = nn.Conv2d(ch, inner, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, dim_head, context_dim)])
+        self.proj_out = nn.Conv2d(inner, ch, 1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.op = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
+
+
+class Upsample(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+
+# ----------------------------------------------------------------------------- packed fp16 weights
+class _Packed:
+    """fp16 GEMM operands derived from the fp32 parameters (rebuilt when a parameter changes)."""
+
+    def __init__(self, model):
+        self.key = tuple((p.data_ptr(), p._version) for p in model.parameters())
+        self.w = {}
+
+    def conv(self, m):
+        k = id(m)
+        if k not in self.w:
+            w = m.weight.detach()
+            co, ci, kh, kw = w.shape
+            if ci % 8:  # pad the input channels to a multiple of 8 (TMA needs 16-byte rows)
+                w = torch.cat([w, w.new_zeros(co, 8 - ci % 8, kh, kw)], 1)
+            self.w[k] = (w.permute(0, 2, 3, 1).reshape(co, -1).to(_f16).contiguous(),
+                         None if m.bias is None else m.bias.detach().to(_f32).contiguous())
+        return self.w[k]
+
+    def linear(self, m):
+        k = id(m)
+        if k not in self.w:
+            self.w[k] = (m.weight.detach().to(_f16).contiguous(),
+                         None if m.bias is None else m.bias.detach().to(_f32).contiguous())
+        return self.w[k]
+
+    def qkv(self, attn):
+        k = ("qkv", id(attn))
+        if k not in self.w:
+            self.w[k] = torch.cat([attn.to_q.weight, attn.to_k.weight, attn.to_v.weight], 0).detach().to(_f16).contiguous()
+        return self.w[k]
+
+    def norm(self, m):
+        k = id(m)
+        if k not in self.w:
+            self.w[k] = (m.weight.detach().to(_f32).contiguous(), m.bias.detach().to(_f32).contiguous())
+        return self.w[k]
+
+
+class UNetModel(nn.Module):
+    def __init__(self, image_size=32, in_channels=8, out_channels=4, model_channels=320, attention_resolutions=(4, 2, 1),
+                 num_res_blocks=2, channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True,
+                 transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False, **unused):
+        super().__init__()
+        if not use_spatial_transformer or transformer_depth != 1 or legacy:
+            raise NotImplementedError("only the Zero123 configuration (spatial transformers, depth 1, legacy=False) is built")
+        self.in_channels, self.out_channels, self.model_channels = in_channels, out_channels, model_channels
+        self.num_heads, self.context_dim = num_heads, context_dim
+        mc, ted = model_channels, model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(mc, ted), nn.SiLU(), nn.Linear(ted, ted))
+        self.input_blocks = nn.ModuleList([nn.Sequential(nn.Conv2d(in_channels, mc, 3, padding=1))])
+        chans, ch, ds = [mc], mc, 1
+        st = lambda c: SpatialTransformer(c, num_heads, c // num_heads, context_dim)
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, ted, mult * mc)]
+                ch = mult * mc
+                if ds in attention_resolutions:
+                    layers.append(st(ch))
+                self.input_blocks.append(nn.Sequential(*layers))
+                chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(nn.Sequential(Downsample(ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = nn.Sequential(ResBlock(ch, ted, ch), st(ch), ResBlock(ch, ted, ch))
+        self.output_blocks = nn.ModuleList()
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [ResBlock(ch + chans.pop(), ted, mc * mult)]
+                ch = mc * mult
+                if ds in attention_resolutions:
+                    layers.append(st(ch))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch))
+                    ds //= 2
+                self.output_blocks.append(nn.Sequential(*layers))
+        self.out = nn.Sequential(_gn(ch), nn.SiLU(), nn.Conv2d(mc, out_channels, 3, padding=1))
+        self._packed = None
+
+    # ------------------------------------------------------------------ executor
+    def _pk(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._packed.key != key:
+            self._packed = _Packed(self)
+        return self._packed
+
+    def _conv3(self, pk, x, B, H, W, C, conv, gn=None, act=False, stride=1, up=False, residual=None):
+        g = None
+        if gn is not None:
+            mean, rstd = A.groupnorm_stats(x, B, H * W, C, 32, gn.eps)
+            gamma, beta = pk.norm(gn)
+            g = (mean, rstd, 32, gamma, beta)
+        a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, 3, stride, up, g, act)
+        w, b = pk.conv(conv)
+        return A.gemm(a, w, bias=b, residual=residual), Ho, Wo
+
+    def _resblock(self, pk, blk, x, B, H, W, emb_act):
+        C, Co = blk.channels, blk.out_channels
+        h, _, _ = self._conv3(pk, x, B, H, W, C, blk.in_layers[2], gn=blk.in_layers[0], act=True)
+        we, be = pk.linear(blk.emb_layers[1])
+        A.add_channel_bias(h, A.gemm(emb_act, we, bias=be), B, H * W, Co)
+        if isinstance(blk.skip_connection, nn.Identity):
+            skip = x
+        else:
+            ws, bs = pk.conv(blk.skip_connection)
+            skip = A.gemm(x, ws, bias=bs)
+        out, _, _ = self._conv3(pk, h, B, H, W, Co, blk.out_layers[3], gn=blk.out_layers[0], act=True, residual=skip)
+        return out, Co
+
+    def _attention(self, pk, attn, xn, B, N, C, residual):
+        """Self-attention on layer-normed tokens xn [B*N, C]; returns to_out(...) + residual."""
+        H, d = attn.heads, attn.dim_head
+        qkv = A.gemm(xn, pk.qkv(attn))                                   # [B*N, 3C]
+        s = torch.empty(B * H, N, N, dtype=_f16, device=xn.device)
+        q, k = qkv[:, :C], qkv[:, C:2 * C]
+        A.bgemm(q, k, s, H, B, (d, N * 3 * C), (d, N * 3 * C), (N * N, H * N * N), N, N, d, 3 * C, 3 * C, N, alpha=d ** -0.5)
+        p = A.softmax_rows(s)
+        vt = A.transpose_tokens(qkv[:, 2 * C:].contiguous(), B, N, C)      # [B, C, N]
+        o = torch.empty(B * N, C, dtype=_f16, device=xn.device)
+        A.bgemm(p, vt, o, H, B, (N * N, H * N * N), (d * N, C * N), (d, N * C), N, d, N, N, N, C)
+        wo, bo = pk.linear(attn.to_out[0])
+        return A.gemm(o, wo, bias=bo, residual=residual)
+
+    def _cross_attention(self, pk, blk, h, ctx16, B, N, C):
+        attn = blk.attn2
+        T = ctx16.shape[0] // B
+        wo, bo = pk.linear(attn.to_out[0])
+        if T == 1:  # one key: softmax == 1, output = to_out(to_v(ctx)) for every query token
+            wv, _ = pk.linear(attn.to_v)
+            o = A.gemm(A.gemm(ctx16, wv), wo, bias=bo)                      # [B, C]
+            return A.add_channel_bias(h, o, B, N, C)
+        H, d = attn.heads, attn.dim_head
+        xn = A.layernorm(h, *pk.norm(blk.norm2), eps=blk.norm2.eps)
+        q = A.gemm(xn, pk.linear(attn.to_q)[0])
+        k = A.gemm(ctx16, pk.linear(attn.to_k)[0])                          # [B*T, C]
+        v = A.gemm(ctx16, pk.linear(attn.to_v)[0])
+        s = torch.empty(B * H, N, T, dtype=_f16, device=h.device)
+        A.bgemm(q, k, s, H, B, (d, N * C), (d, T * C), (N * T, H * N * T), N, T, d, C, C, T, alpha=d ** -0.5)
+        p = A.softmax_rows(s)
+        Tp = (T + 7) // 8 * 8                                               # TMA rows need 16-byte strides
+        pp = torch.zeros(B * H, N, Tp, dtype=_f16, device=h.device)
+        pp[:, :, :T] = p
+        vt = torch.zeros(B, C, Tp, dtype=_f16, device=h.device)
+        vt[:, :, :T] = A.transpose_tokens(v, B, T, C)
+        o = torch.empty(B * N, C, dtype=_f16, device=h.device)
+        A.bgemm(pp, vt, o, H, B, (N * Tp, H * N * Tp), (d * Tp, C * Tp), (d, N * C), N, d, Tp, Tp, Tp, C)
+        return A.gemm(o, wo, bias=bo, residual=h)
+
+    def _transformer(self, pk, st, x, B, H, W, C, ctx16):
+        N = H * W
+        mean, rstd = A.groupnorm_stats(x, B, N, C, 32, st.norm.eps)
+        a, _, _ = A.norm_act_im2col(x, B, H, W, C, 1, 1, False, (mean, rstd, 32, *pk.norm(st.norm)), False)
+        wi, bi = pk.conv(st.proj_in)
+        h = A.gemm(a, wi, bias=bi)
+        blk = st.transformer_blocks[0]
+        h = self._attention(pk, blk.attn1, A.layernorm(h, *pk.norm(blk.norm1), eps=blk.norm1.eps), B, N, C, h)
+        h = self._cross_attention(pk, blk, h, ctx16, B, N, C)
+        w1, b1 = pk.linear(blk.ff.net[0].proj)
+        w2, b2 = pk.linear(blk.ff.net[2])
+        g = A.geglu(A.gemm(A.layernorm(h, *pk.norm(blk.norm3), eps=blk.norm3.eps), w1, bias=b1))
+        h = A.gemm(g, w2, bias=b2, residual=h)
+        wo, bo = pk.conv(st.proj_out)
+        return A.gemm(h, wo, bias=bo, residual=x)
+
+    def _run_block(self, pk, seq, x, B, H, W, C, emb_act, ctx16):
+        for layer in seq:
+            if isinstance(layer, ResBlock):
+                x, C = self._resblock(pk, layer, x, B, H, W, emb_act)
+            elif isinstance(layer, SpatialTransformer):
+                x = self._transformer(pk, layer, x, B, H, W, C, ctx16)
+            elif isinstance(layer, Downsample):
+                x, H, W = self._conv3(pk, x, B, H, W, C, layer.op, stride=2)
+            elif isinstance(layer, Upsample):
+                x, H, W = self._conv3(pk, x, B, H, W, C, layer.conv, up=True)
+            elif isinstance(layer, nn.Conv2d):
+                x, H, W = self._conv3(pk, x, B, H, W, C, layer)
+                C = layer.out_channels
+            else:
+                raise TypeError(type(layer))
+        return x, H, W, C
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        assert y is None, "the Zero123 UNet is not class-conditional"
+        pk = self._pk()
+        B, Cin, H, W = x.shape
+        C = (Cin + 7) // 8 * 8
+        h = A.nchw_to_cl(x, torch.zeros(B * H * W, C, dtype=_f16, device=x.device))
+        t_emb = A.timestep_embedding(timesteps, self.model_channels)
+        w0, b0 = pk.linear(self.time_embed[0])
+        w2, b2 = pk.linear(self.time_embed[2])
+        emb = A.gemm(A.gemm(t_emb, w0, bias=b0, act=1), w2, bias=b2)
+        emb_act = A.silu(emb)                                               # every ResBlock starts emb_layers with SiLU
+        ctx16 = context.reshape(-1, context.shape[-1]).to(_f16).contiguous()
+        hs = []
+        for seq in self.input_blocks:
+            h, H, W, C = self._run_block(pk, seq, h, B, H, W, C, emb_act, ctx16)
+            hs.append((h, C))
+        h, H, W, C = self._run_block(pk, self.middle_block, h, B, H, W, C, emb_act, ctx16)
+        for seq in self.output_blocks:
+            skip, Cs = hs.pop()
+            cat = torch.empty(B * H * W, C + Cs, dtype=_f16, device=h.device)
+            A.copy_channels(h, cat, 0)
+            A.copy_channels(skip, cat, C)
+            h, H, W, C = self._run_block(pk, seq, cat, B, H, W, C + Cs, emb_act, ctx16)
+        out, _, _ = self._conv3(pk, h, B, H, W, C, self.out[2], gn=self.out[0], act=True)
+        return A.cl_to_nchw(out, B, self.out_channels, H, W)
