@@ -276,8 +276,9 @@ int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, i
 int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, float* mean, float* rstd,
                           o2345_stream_t stream);
 /* out [B*Ho*Wo, k*k*C] (column order ky,kx,c) = patches of f(x), f = GroupNorm(+SiLU if act) when mean != NULL.
- * upsample != 0: nearest x2 replication of x before the convolution.  Zero padding k/2. */
-int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample,
+ * upsample != 0: nearest x2 replication of x before the convolution.  Zero padding k/2 on the high side and
+ * pad_lo on the low side (pad_lo < 0: k/2; pad_lo = 0 reproduces the VAE encoder's F.pad(x, (0,1,0,1))). */
+int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample, int pad_lo,
                           const float* mean, const float* rstd, int G, const float* gamma, const float* beta, int act,
                           void* out, o2345_stream_t stream);
 int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,

@@ -55,7 +55,7 @@ __global__ void groupnorm_stats_kernel(const __half* __restrict__ x, int HW, int
 __global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int KS, int stride, int up,
                                        const float* __restrict__ mean, const float* __restrict__ rstd, int G,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                                       __half* __restrict__ out, int Ho, int Wo) {
+                                       __half* __restrict__ out, int Ho, int Wo, int pad) {
   const int c8 = C >> 3;  // 8 channels (16 bytes) per thread
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)B * Ho * Wo * KS * KS * c8;
@@ -64,7 +64,7 @@ __global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int 
   int kk = (int)((idx / c8) % (KS * KS));
   int64_t pix = idx / ((int64_t)c8 * KS * KS);
   int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((int64_t)Wo * Ho));
-  int ky = kk / KS, kx = kk % KS, pad = KS / 2;
+  int ky = kk / KS, kx = kk % KS;
   int Hin = up ? 2 * H : H, Win = up ? 2 * W : W;
   int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
   uint4 o = make_uint4(0, 0, 0, 0);
@@ -233,17 +233,17 @@ extern "C" int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G,
   return O2345_OK;
 }
 
-extern "C" int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample,
+extern "C" int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample, int pad_lo,
                                      const float* mean, const float* rstd, int G, const float* gamma, const float* beta,
                                      int act, void* out, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && out && (C % 8) == 0 && (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "bad arguments");
   O2345_CHECK_ARG(!mean || (rstd && gamma && beta && G > 0 && C % G == 0), "incomplete GroupNorm arguments");
   int Hin = upsample ? 2 * H : H, Win = upsample ? 2 * W : W;
-  int pad = ksize / 2;
-  int Ho = (Hin + 2 * pad - ksize) / stride + 1, Wo = (Win + 2 * pad - ksize) / stride + 1;
+  int pad_hi = ksize / 2, pad = pad_lo < 0 ? ksize / 2 : pad_lo;   // pad_lo = 0: the VAE's (0,1,0,1) down-sampling pad
+  int Ho = (Hin + pad + pad_hi - ksize) / stride + 1, Wo = (Win + pad + pad_hi - ksize) / stride + 1;
   int64_t total = (int64_t)B * Ho * Wo * ksize * ksize * (C / 8);
   norm_act_im2col_kernel<<<cdiv(total, 256), 256, 0, ST>>>((const __half*)x, B, H, W, C, ksize, stride, upsample, mean, rstd, G,
-                                                           gamma, beta, act, (__half*)out, Ho, Wo);
+                                                           gamma, beta, act, (__half*)out, Ho, Wo, pad);
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -45,14 +45,15 @@ def groupnorm_stats(x, B, HW, C, G=32, eps=1e-5):
     return mean, rstd
 
 
-def norm_act_im2col(x, B, H, W, C, ksize=3, stride=1, upsample=False, gn=None, act=False):
+def norm_act_im2col(x, B, H, W, C, ksize=3, stride=1, upsample=False, gn=None, act=False, pad_lo=-1):
     """gn = (mean, rstd, G, gamma, beta) or None.  Returns ([B*Ho*Wo, k*k*C] fp16, Ho, Wo)."""
     Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
-    pad = ksize // 2
-    Ho, Wo = (Hin + 2 * pad - ksize) // stride + 1, (Win + 2 * pad - ksize) // stride + 1
+    pad_hi = ksize // 2
+    pad = pad_hi if pad_lo < 0 else pad_lo
+    Ho, Wo = (Hin + pad + pad_hi - ksize) // stride + 1, (Win + pad + pad_hi - ksize) // stride + 1
     out = torch.empty(B * Ho * Wo, ksize * ksize * C, dtype=_f16, device=x.device)
     mean, rstd, G, gamma, beta = gn if gn is not None else (None, None, 0, None, None)
-    L.call("o2345_norm_act_im2col", _v(x), B, H, W, C, ksize, stride, int(upsample), _v(mean), _v(rstd), G, _v(gamma), _v(beta),
+    L.call("o2345_norm_act_im2col", _v(x), B, H, W, C, ksize, stride, int(upsample), int(pad_lo), _v(mean), _v(rstd), G, _v(gamma), _v(beta),
            int(act), _v(out), _stream())
     return out, Ho, Wo
 

@@ -324,3 +324,22 @@ def unet_state(seed=0, gain=0.7):
         else:
             sd[k] = 0.02 * rng.standard_normal(shp, dtype=np.float32)
     return sd
+
+
+def vae_state(seed=10, gain=0.7):
+    """State dict of the AutoencoderKL (reference keys, 83.7 M parameters), same recipe as unet_state."""
+    import torch
+    from .autoencoder import AutoencoderKL
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in AutoencoderKL().state_dict().items()}
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        if len(shp) >= 2:
+            sd[k] = rng.standard_normal(shp, dtype=np.float32) * np.float32(gain / math.sqrt(int(np.prod(shp[1:]))))
+        elif "norm" in k:
+            sd[k] = (1.0 + 0.1 * rng.standard_normal(shp, dtype=np.float32)) if k.endswith("weight") else \
+                (0.05 * rng.standard_normal(shp, dtype=np.float32))
+        else:
+            sd[k] = 0.02 * rng.standard_normal(shp, dtype=np.float32)
+    return sd
