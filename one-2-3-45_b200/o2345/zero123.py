@@ -1,0 +1,193 @@
+"""Zero123 multi-view generation on the o2345 kernels: LatentDiffusion (inference subset) + the run.py stage logic.
+
+Mirrors, with the same call signatures:
+  * LatentDiffusion.apply_model / encode_first_stage / decode_first_stage / get_learned_conditioning /
+    cc_projection / ema_scope / register_schedule     (reference ldm/models/diffusion/ddpm.py:126-193,526,619-630,
+    763-860,888-984,1441-1474) -- the `hybrid` conditioning of configs/sd-objaverse-finetune-c_concat-256.yaml;
+  * sample_model_batch, predict_stage1_gradio, zero123_infer            (reference utils/zero123_utils.py:60-178);
+  * stage1_run / stage2_run view bookkeeping                             (reference run.py:18-54).
+Out of scope here: the CLIP image tower (row A8) -- `cond_stage_model` is a pluggable
+callable, by default a seeded stand-in embedding -- and the LoFTR elevation search (the polar angle is an input).
+Checkpoint keys: `model.diffusion_model.*`, `first_stage_model.*`, `cc_projection.*` load directly.
+"""
+from __future__ import annotations
+
+import contextlib
+import json
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops_a as A
+from . import synthetic as S
+from .autoencoder import AutoencoderKL
+from .ddim import DDIMSampler
+from .unet import UNetModel
+
+
+class _DiffusionWrapper(nn.Module):
+    def __init__(self, unet):
+        super().__init__()
+        self.diffusion_model = unet
+        self.conditioning_key = "hybrid"
+
+
+class LatentDiffusion(nn.Module):
+    def __init__(self, unet_config=None, first_stage_config=None, scale_factor=0.18215, timesteps=1000,
+                 linear_start=0.00085, linear_end=0.0120, cond_stage_model=None):
+        super().__init__()
+        self.model = _DiffusionWrapper(UNetModel(**(unet_config or {})))
+        self.first_stage_model = AutoencoderKL(**(first_stage_config or {}))
+        self.cc_projection = nn.Linear(772, 768)
+        self.scale_factor, self.num_timesteps, self.parameterization = scale_factor, timesteps, "eps"
+        self.cond_stage_model = cond_stage_model
+        # register_schedule('linear'), reference ddpm.py:126-178 + util.py:21-25: fp64 math, fp32 buffers
+        betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=np.float64) ** 2
+        ac = np.cumprod(1.0 - betas, axis=0)
+        f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+        self.register_buffer("betas", f32(betas))
+        self.register_buffer("alphas_cumprod", f32(ac))
+        self.register_buffer("alphas_cumprod_prev", f32(np.append(1.0, ac[:-1])))
+        self._cc = None
+
+    @property
+    def device(self):
+        return self.betas.device
+
+    def half(self):
+        """`model.half()` in the reference (zero123_utils.py:45) also rounds the schedule buffers to fp16, and the
+        sampler then reads those.  Weights are already consumed as fp16 by the kernels."""
+        for n in ("betas", "alphas_cumprod", "alphas_cumprod_prev"):
+            getattr(self, n).data = getattr(self, n).data.half()
+        return self
+
+    @contextlib.contextmanager
+    def ema_scope(self, context=None):
+        yield None  # EMA weights are what gets loaded; there is nothing to swap at inference
+
+    @torch.no_grad()
+    def apply_model(self, x_noisy, t, cond, return_ids=False):
+        xc = torch.cat([x_noisy] + cond["c_concat"], dim=1)
+        cc = torch.cat(cond["c_crossattn"], 1)
+        return self.model.diffusion_model(xc, t, context=cc)
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        return self.first_stage_model.encode(x)
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        return self.first_stage_model.decode(1. / self.scale_factor * z)
+
+    @torch.no_grad()
+    def get_learned_conditioning(self, c):
+        if self.cond_stage_model is None:
+            g = torch.Generator().manual_seed(7)            # stand-in for FrozenCLIPImageEmbedder (row A8, not built)
+            return torch.randn(c.shape[0], 1, 768, generator=g).to(c.device)
+        return self.cond_stage_model(c)
+
+    @torch.no_grad()
+    def project_condition(self, c):
+        """cc_projection: Linear(772 -> 768) on [n,1,772] (reference ddpm.py:526)."""
+        w = self.cc_projection.weight
+        key = (w.data_ptr(), w._version)
+        if self._cc is None or self._cc[0] != key:
+            wp = torch.zeros(768, 776, dtype=torch.float16, device=w.device)
+            wp[:, :772] = w.detach().half()
+            self._cc = (key, wp, self.cc_projection.bias.detach().float().contiguous())
+        n = c.shape[0]
+        cp = torch.zeros(n, 776, dtype=torch.float16, device=c.device)
+        cp[:, :772] = c.reshape(n, 772).half()
+        return A.gemm(cp, self._cc[1], bias=self._cc[2]).float().view(n, 1, 768)
+
+
+@torch.no_grad()
+def sample_model_batch(model, sampler, input_im, xs, ys, n_samples=4, precision='autocast', ddim_eta=1.0, ddim_steps=75,
+                       scale=3.0, h=256, w=256):
+    """reference utils/zero123_utils.py:60-98; returns images in [0,1], float32, on the host."""
+    with model.ema_scope():
+        c = model.get_learned_conditioning(input_im).tile(n_samples, 1, 1)
+        T = [[np.radians(x), np.sin(np.radians(y)), np.cos(np.radians(y)), 0] for x, y in zip(xs, ys)]
+        T = torch.tensor(np.array(T))[:, None, :].float().to(c.device)
+        c = model.project_condition(torch.cat([c, T], dim=-1))
+        cond = {'c_crossattn': [c],
+                'c_concat': [model.encode_first_stage(input_im).mode().detach().repeat(n_samples, 1, 1, 1)]}
+        uc = None
+        if scale != 1.0:
+            uc = {'c_concat': [torch.zeros(n_samples, 4, h // 8, w // 8).to(c.device)], 'c_crossattn': [torch.zeros_like(c)]}
+        samples, _ = sampler.sample(S=ddim_steps, conditioning=cond, batch_size=n_samples, shape=[4, h // 8, w // 8],
+                                    verbose=False, unconditional_guidance_scale=scale, unconditional_conditioning=uc,
+                                    eta=ddim_eta, x_T=None)
+        x = model.decode_first_stage(samples)
+        return torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0).cpu()
+
+
+DELTA_X_1_8 = [0] * 4 + [30] * 4 + [-30] * 4
+DELTA_Y_1_8 = [0 + 90 * (i % 4) if i < 4 else 30 + 90 * (i % 4) for i in range(8)] + [30 + 90 * (i % 4) for i in range(4)]
+DELTA_X_2, DELTA_Y_2 = [-10, 10, 0, 0], [0, 0, -10, 10]
+
+
+def _to_uint8(img):
+    """(x * 255).astype(uint8): the PNG the reference writes between the stages (zero123_utils.py:125-129)."""
+    return (255.0 * img.numpy().transpose(1, 2, 0)).astype(np.uint8)
+
+
+def _as_input(u8, whiten):
+    a = u8.astype(np.float32)
+    if whiten:                       # stage-2 inputs: >= 253 -> 255 (zero123_utils.py:145-147)
+        a[a >= 253.0] = 255.0
+    return torch.from_numpy(a / 255.0).permute(2, 0, 1)[None] * 2 - 1
+
+
+@torch.no_grad()
+def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=50, scale=3.0, exp_dir=None, device="cuda"):
+    """run.py's stage1_run + stage2_run (reference run.py:18-54) with the elevation given instead of estimated:
+    10 sampler calls = 2 x 76 + 8 x 49 UNet iterations at batch 8.  Returns (stage1 dict id -> uint8 image,
+    stage2 dict 'i_j' -> uint8 image, pose dict).  With exp_dir the same PNG files and pose.json are written."""
+    dev = torch.device(device)
+    inp = _as_input(input_u8, False).to(dev)
+    stage1, stage2 = {}, {}
+
+    def stage1_call(adjust):
+        sampler = DDIMSampler(model)
+        imgs = sample_model_batch(model, sampler, inp, [DELTA_X_1_8[i] for i in adjust], [DELTA_Y_1_8[i] for i in adjust],
+                                  n_samples=len(adjust), ddim_steps=ddim_steps, scale=scale)
+        for k, i in enumerate(adjust):
+            stage1[i] = _to_uint8(imgs[k])
+
+    def stage2_call(i):
+        sampler = DDIMSampler(model)
+        imgs = sample_model_batch(model, sampler, _as_input(stage1[i], True).to(dev), DELTA_X_2, DELTA_Y_2, n_samples=4,
+                                  ddim_steps=stage2_steps, scale=scale)
+        for j in range(4):
+            stage2[f"{i}_{j}"] = _to_uint8(imgs[j])
+
+    stage1_call(list(range(4)))
+    stage2_call(0)
+    pose = S.pose_json(float(polar_angle))
+    second = list(range(4, 8)) if polar_angle <= 75 else list(range(8, 12))
+    stage1_call(second)
+    for i in ([1, 2, 3] + second):
+        stage2_call(i)
+    if exp_dir is not None:
+        from PIL import Image
+        os.makedirs(os.path.join(exp_dir, "stage1_8"), exist_ok=True)
+        os.makedirs(os.path.join(exp_dir, "stage2_8"), exist_ok=True)
+        for i, im in stage1.items():
+            Image.fromarray(im).save(os.path.join(exp_dir, "stage1_8", f"{i}.png"))
+        for k, im in stage2.items():
+            Image.fromarray(im).save(os.path.join(exp_dir, "stage2_8", f"{k}.png"))
+        json.dump(pose, open(os.path.join(exp_dir, "pose.json"), "w"), indent=4)
+    return stage1, stage2, pose
+
+
+def build_zero123(device, seed=0):
+    """LatentDiffusion with seeded random weights (no checkpoint exists offline)."""
+    m = LatentDiffusion()
+    m.model.diffusion_model.load_state_dict({k: torch.from_numpy(v) for k, v in S.unet_state(seed).items()})
+    m.first_stage_model.load_state_dict({k: torch.from_numpy(v) for k, v in S.vae_state(seed + 10).items()})
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m.to(device)
