@@ -131,6 +131,12 @@ def reset_launches():
     _launches = 0
 
 
+def add_launches(n: int):
+    """Kernels replayed by a captured CUDA graph (counted once at capture time)."""
+    global _launches
+    _launches += n
+
+
 def launches() -> int:
     """Number of o2345 kernels launched since reset_launches() (bench.py's gpu_launches)."""
     return _launches

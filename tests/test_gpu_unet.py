@@ -2,7 +2,7 @@
 
 Tolerance: the reference itself runs this model in fp16 under autocast (fp32 GroupNorm / LayerNorm / softmax); the
 golden vector is the reference's fp32 CPU output.  fp16 storage of ~60 layers gives ~1e-2 relative deviations, so
-the bar is max |err| < 0.06 and mean |err| < 0.012 on an output of std 0.38 (a wrong layer gives O(1))."""
+the bar is max |err| < 0.02 and mean |err| < 0.004 on an output of std 0.38 (measured: 0.002 / 0.0004; a wrong layer gives O(1))."""
 import os
 
 import numpy as np
@@ -35,7 +35,7 @@ def test_unet_matches_reference_golden(unet, gold):
     assert e.shape == (2, 4, 32, 32) and e.dtype == torch.float32
     err = (e.cpu() - torch.from_numpy(gold["unet_eps"])).abs()
     print("unet: max err", float(err.max()), "mean err", float(err.mean()))
-    assert float(err.max()) < 0.06 and float(err.mean()) < 0.012
+    assert float(err.max()) < 0.02 and float(err.mean()) < 0.004
 
 
 def test_unet_batch8_is_consistent_with_batch2(unet):
@@ -44,9 +44,13 @@ def test_unet_batch8_is_consistent_with_batch2(unet):
     x = torch.randn(8, 8, 32, 32, device="cuda", generator=g)
     t = torch.full((8,), 501, device="cuda")
     ctx = torch.randn(8, 1, 768, device="cuda", generator=g)
-    full = unet(x, t, ctx)
-    half = torch.cat([unet(x[:4], t[:4], ctx[:4]), unet(x[4:], t[4:], ctx[4:])])
+    full = unet(x, t, ctx).clone()          # graph replays reuse one static output buffer per input shape
+    half = torch.cat([unet(x[:4], t[:4], ctx[:4]).clone(), unet(x[4:], t[4:], ctx[4:]).clone()])
     assert float((full - half).abs().max()) < 2e-3
+    unet.use_cuda_graph = False              # eager launches and graph replay must agree bit for bit
+    eager = unet(x, t, ctx)
+    unet.use_cuda_graph = True
+    assert torch.equal(eager, full)
 
 
 def test_ddim_sampler_matches_reference_trajectory(gold):
