@@ -1,18 +1,18 @@
-"""bench.py -- volume-render throughput of the reconstruction hot path on B200.
+"""bench.py -- One-2-3-45 hot paths on B200: sec/mesh end to end, and volume-render M rays/sec.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Metric (BASELINE.json): "volume-render M rays/sec".  One step = GenericTrainer mode='val' on one scene of
-BASELINE configs[1]'s reconstruction half: 32 source views of 256x256 -> FeatureNet -> 96^3 cost volume ->
-sparse U-Net -> hierarchical ray march of the full 256x256 query image (65 536 rays x (64+64) samples x 32
-views), fp32.  `value` keeps the scene resident in HBM; `e2e` runs the same step through the public call
-(`trainer(sample, mode='val')`) starting from pinned HOST buffers and ending with the rendered colour /
-depth / normal images back on the host.  N > 1: one process per GPU, one independent scene per rank
-(weak scaling, no data-path collective; NCCL only broadcasts the weights once and reduces the timing).
-
-NOTE: the other half of BASELINE's metric string (sec/mesh end to end) needs the Zero123 DDIM stage
-(SURVEY.md rows A1-A9), which is not built yet; the reconstruction-only mesh time is reported as the
-informational key "export_mesh_s" and is NOT a sec/mesh claim.
+Headline metric (BASELINE.json, configs[1]): "sec/mesh end-to-end (256x256 in)".  One step = one 256x256 input
+image -> Zero123 stage 1 + stage 2 (10 DDIM sampler calls = 2x76 + 8x49 = 544 UNet iterations at the CFG batch
+of 8, fp16 tensor-core GEMMs with fp32 accumulate; 10 VAE encodes, 40 VAE decodes) -> 32 views -> FeatureNet ->
+96^3 cost volume -> sparse U-Net -> 256^3 SDF grid -> marching cubes -> vertex colours -> mesh arrays on the host
+(`o2345.pipeline.image_to_mesh`).  Not inside the step (out of scope): SAM / rembg
+preprocessing, the CLIP image tower (a fixed embedding stands in) and the LoFTR elevation search (polar angle 60).
+`value` is timed on the device with CUDA events; `e2e` is the wall clock of the same public call starting from a
+pinned host image and ending with the mesh on the host (the pipeline itself moves the generated views through the
+host as uint8, as the reference's PNG hand-off does).  The second BASELINE metric, "volume-render M rays/sec", is
+reported under "rays" with its own roofline (GenericTrainer mode='val' on 65 536 rays x (64+64) samples x 32 views).
+N > 1: one process per GPU, one independent image per rank (weak scaling, no data-path collective).
 """
 from __future__ import annotations
 
@@ -36,18 +36,20 @@ H = W = 256
 N_VIEWS = 32
 VOL = 96
 N_RAYS = H * W
-N_S, N_I = 64, 64
-CHUNK = 8192            # rays per render() call (the reference uses 512; results are chunk-invariant)
+CHUNK = 8192
 MESH_RES = 256
-CONFIG = {"workload": "configs[1] reconstruction half: 32 views 256x256 -> 96^3 volume -> render 65536 rays x (64+64) samples",
-          "views": N_VIEWS, "vol_dim": VOL, "rays": N_RAYS, "samples": [N_S, N_I], "chunk_rays": CHUNK,
-          "l2": "inputs larger than L2 (feature maps 470 MB + channel-last maps 503 MB + volume 57 MB per step)",
-          "parallelism": "one scene per GPU"}
-# algorithmic work of SURVEY.md section 8(d)
+UNET_ITERS = 2 * 76 + 8 * 49
+CONFIG = {"workload": "configs[1]: single 256x256 image -> mesh: Zero123 75/50-step DDIM fp16 (544 UNet iterations at batch 8) "
+                      "+ 96^3 cost volume + 256^3 SDF grid + marching cubes, 1 image per GPU",
+          "views": N_VIEWS, "vol_dim": VOL, "mesh_resolution": MESH_RES, "ddim_steps": [75, 50], "cfg_scale": 3.0,
+          "l2": "inputs larger than L2 (1.72 GB fp16 UNet weights stream every iteration; 470 MB feature maps)",
+          "not_in_step": "SAM/rembg, CLIP image tower (fixed embedding), LoFTR elevation search (polar angle 60)",
+          "parallelism": "one image per GPU"}
+# algorithmic work, SURVEY.md section 8(d)
+UNET_FLOP_PER_SAMPLE = 176.3e9
 FLOP_SDF_FWD = 2 * 41856.0
 FLOP_SDF_BWD = 2 * (128 * 144 + 128 * 39)
-RAY_FLOP = 211e6
-RAY_GATHER_BYTES = 4.0e6
+RAY_FLOP, RAY_GATHER_BYTES = 211e6, 4.0e6
 
 
 def peaks():
@@ -72,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -85,23 +87,21 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        ok = [r for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        sm = [float(r[1]) for r in ok]
+        mx = [float(r[2]) for r in ok]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in ok for i in range(4) if r[4 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_scene(dev, seed):
+def input_image(seed):
     from o2345 import synthetic as S
-    from o2345.pipeline import _sample_from
-    cams = S.scene_cameras(S.pose_json(60.0), n_src=N_VIEWS, img_wh=(W, H))
-    imgs = S.images(N_VIEWS + 1, H, W, seed=seed)
-    return _sample_from(cams, imgs, dev, H, W, pin=True)
+    return (S.images(1, H, W, seed=seed)[0].transpose(1, 2, 0) * 255.0).astype(np.uint8)
 
 
-def ev_time(fn, stream=None):
+def ev_time(fn):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     out = fn()
@@ -112,33 +112,25 @@ def ev_time(fn, stream=None):
 
 def run_gpu(args):
     import torch.distributed as dist
-    from o2345 import _lib, synthetic as S
-    from o2345.pipeline import build_networks
+    from o2345 import _lib, sharding, synthetic as S
+    from o2345.pipeline import build_networks, image_to_mesh
+    from o2345.zero123 import build_zero123
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from o2345 import sharding
     tr = build_networks(dev, vol_dim=VOL, states=S.all_states(0), perturb=0.0)
+    z123 = build_zero123(dev, seed=0).half()            # `--half_precision`: fp16-rounded schedule buffers
     # the only collective on the path: weights from rank 0 over NVLink (no-op at N = 1)
     sharding.broadcast_module_weights([tr.pyramid_feature_network_geometry_lod0, tr.sdf_network_lod0,
-                                       tr.rendering_network_lod0, tr.variance_network_lod0], src=0)
-    sample, host, host_rays = build_scene(dev, seed=1234 + rank)
-    tr_val = lambda smp: tr.val_step(smp, perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio_lod0=1.0, chunk_size=CHUNK)
-
-    def step_resident():
-        return tr_val_device(tr, sample)
-
-    def step_e2e():
-        smp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        smp["rays"] = {k: v.to(dev, non_blocking=True) for k, v in host_rays.items()}
-        smp["batch_idx"], smp["meta"] = sample["batch_idx"], sample["meta"]
-        return tr_val(smp)                      # ends with .cpu() of colour / depth / normal
+                                       tr.rendering_network_lod0, tr.variance_network_lod0, z123], src=0)
+    img_host = torch.from_numpy(input_image(4321 + rank)).pin_memory()
+    step = lambda: image_to_mesh(z123, tr, img_host.numpy(), polar_angle=60, resolution=MESH_RES)
 
     for _ in range(args.warmup):
-        step_resident()
+        step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -146,222 +138,214 @@ def run_gpu(args):
     clocks.start()
     _lib.reset_launches()
     torch.cuda.synchronize()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
     t0.record()
     for _ in range(args.steps):
-        step_resident()
+        mesh = step()
     t1.record()
     torch.cuda.synchronize()
+    wall_s = time.perf_counter() - w0
     launches = _lib.launches()
-    ms = t0.elapsed_time(t1)
     clk = clocks.stop()
-    # e2e: same step from pinned host buffers, results read back to the host every step
-    step_e2e()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    ms, e2e_ms = sharding.max_over_ranks([ms, e2e_s * 1e3], dev)
-    out = None
+    ms, e2e_ms = sharding.max_over_ranks([t0.elapsed_time(t1), wall_s * 1e3], dev)
     if rank == 0:
         pk = peaks()
-        rays_per_s = world * args.steps * N_RAYS / (ms * 1e-3)
-        e2e_rays = world * args.steps * N_RAYS / (e2e_ms * 1e-3)
-        h2d = sum(v.numel() * v.element_size() for v in list(host.values()) + list(host_rays.values()))
-        d2h = N_RAYS * (3 + 1 + 3) * 4
-        roof, mesh_s = kernel_rooflines(tr, sample, dev, pk)
-        out = {"metric": "volume-render M rays/sec", "value": rays_per_s / 1e6, "unit": "M rays/s", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        sec_per_mesh = ms * 1e-3 / (args.steps * world)
+        out = {"metric": "sec/mesh end-to-end (256x256 in)", "value": sec_per_mesh, "unit": "s/mesh", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": False,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": CONFIG,
                "clocks": clk, "gpu_launches": launches,
-               "e2e": {"value": e2e_rays / 1e6, "unit": "M rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "roofline": roof, "export_mesh_s": mesh_s, "peaks": pk["source"]}
+               "e2e": {"value": e2e_ms * 1e-3 / (args.steps * world), "unit": "s/mesh", "h2d_bytes_per_step": int(img_host.numel()),
+                       "d2h_bytes_per_step": int(mesh["vertices"].nbytes + mesh["triangles"].nbytes + mesh["colors"].nbytes)},
+               "mesh": {"vertices": int(len(mesh["vertices"])), "triangles": int(len(mesh["triangles"]))},
+               "peaks": pk["source"]}
+        out.update(stage_breakdown(z123, tr, dev, pk))
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(tr, sample, budget_rays=args.cpu_rays)
+            out["cpu_baseline"] = cpu_reference()
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return out
 
 
-def tr_val_device(tr, sample):
-    """mode='val' with device-resident inputs and outputs (no host copies inside the step)."""
-    imgs, fmaps, cond, sizeW, sizeH = tr._conditional_features(sample)
-    vol, occ = cond['dense_volume_scale0'], cond['valid_mask_volume_scale0']
-    near, far = sample['query_near_far'][0, :1], sample['query_near_far'][0, 1:]
-    ro = sample['rays']['rays_o'][0].reshape(-1, 3)
-    rd = sample['rays']['rays_v'][0].reshape(-1, 3)
-    outs = []
-    for a, b in zip(ro.split(CHUNK), rd.split(CHUNK)):
-        o = tr.sdf_renderer_lod0.render(a, b, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0,
-                                        perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
-                                        conditional_volume=vol, conditional_valid_mask_volume=occ, feature_maps=fmaps,
-                                        color_maps=imgs, w2cs=sample['w2cs'][0], intrinsics=sample['intrinsics'][0],
-                                        img_wh=[sizeW, sizeH], query_c2w=sample['query_c2w'], if_render_with_grad=False)
-        outs.append((o['color_fine'], o['depth']))
-    return outs
+def stage_breakdown(z123, tr, dev, pk):
+    """Per-stage device times, the tensor-core roofline of the dominant kernel (the tcgen05 GEMM inside the UNet)
+    and the volume-rendering throughput with its own roofline."""
+    from o2345 import ops_a
+    from o2345.pipeline import synthetic_sample
+    unet, vae = z123.model.diffusion_model, z123.first_stage_model
+    x = torch.randn(8, 8, 32, 32, device=dev)
+    t = torch.full((8,), 501, device=dev)
+    ctx = torch.randn(8, 1, 768, device=dev)
+    unet(x, t, ctx)
+    ms_unet = float(np.mean([ev_time(lambda: unet(x, t, ctx))[0] for _ in range(10)]))
+    # time spent inside the GEMM kernel during one eager pass (events around every GEMM call)
+    rec = []
+    real_gemm, real_bgemm = ops_a.gemm, ops_a.bgemm
 
-
-def kernel_rooflines(tr, sample, dev, pk):
-    """Times the dominant kernels in isolation with CUDA events (same stream torch launches on)."""
-    from o2345 import ops
-    from o2345.sparse_sdf_network import channel_last_volume
-    imgs, fmaps, cond, sizeW, sizeH = tr._conditional_features(sample)
-    vol, occ = cond['dense_volume_scale0'], cond['valid_mask_volume_scale0']
-    vol_cl = channel_last_volume(vol)
-    near, far = sample['query_near_far'][0, :1], sample['query_near_far'][0, 1:]
-    ro = ops.cf32(sample['rays']['rays_o'][0].reshape(-1, 3))
-    rd = ops.cf32(sample['rays']['rays_v'][0].reshape(-1, 3))
-    R = ro.shape[0]
-    pack = tr.sdf_network_lod0.sdf_layer.packed()
-    # a realistic set of fine samples: run the hierarchical sampling once for the whole image
-    o = tr.sdf_renderer_lod0.render(ro, rd, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0,
-                                    perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
-                                    conditional_volume=vol, conditional_valid_mask_volume=occ, feature_maps=fmaps,
-                                    color_maps=imgs, w2cs=sample['w2cs'][0], intrinsics=sample['intrinsics'][0],
-                                    img_wh=[sizeW, sizeH], query_c2w=sample['query_c2w'])
-    mid = o['mid_z_vals'].contiguous()
-    active = (o['inside_sphere'] > 0).to(torch.uint8).reshape(-1).contiguous()
-    n_act = int(active.sum())
-    src = ops.PointSource.rays(ro, rd, mid)
-    res = {}
-    for name, fn, flop in (
-        ("sdf_query_kernel<grad> (fine pass, 65536x128 samples)",
-         lambda: ops.sdf_query(src, vol_cl, pack, active=active, want_grad=True), n_act * (FLOP_SDF_FWD + FLOP_SDF_BWD)),
-        ("sdf_query_kernel<fwd> (coarse pass, 65536x64 samples)",
-         lambda: ops.sdf_query(ops.PointSource.rays(ro, rd, o['z_vals'][:, ::2].contiguous()), vol_cl, pack), R * 64 * FLOP_SDF_FWD),
-    ):
-        for _ in range(2):
-            fn()
-        ts = [ev_time(fn)[0] for _ in range(5)]
-        res[name] = {"ms": float(np.mean(ts)), "tflops": flop / (np.mean(ts) * 1e-3) / 1e12}
-    views = tr.sdf_renderer_lod0._source_views(fmaps, imgs, sample['w2cs'][0], sample['intrinsics'][0], [sizeW, sizeH])
-    qc = ops.cf32(sample['query_c2w'].reshape(-1, 4, 4)[0, :3, 3])
-    fn = lambda: ops.render_blend(src, active, vol_cl, occ, views, tr.rendering_network_lod0.packed(), query_center=qc)
-    for _ in range(2):
-        fn()
-    ts = [ev_time(fn)[0] for _ in range(5)]
-    nvalid = fn()[1]
-    pairs = int(nvalid.sum())
-    gather = pairs * 4 * 240 + n_act * (8 * 64 + 8 * 4)       # bytes actually requested (valid views only)
-    res["render_blend_kernel (65536x128 samples x 32 views)"] = {
-        "ms": float(np.mean(ts)), "gather_gbs": gather / (np.mean(ts) * 1e-3) / 1e9, "valid_pairs": pairs, "active_samples": n_act}
-    # whole ray march of one image, against SURVEY.md 8(d)'s contract t_roof = max(FLOP/peak, bytes/HBM)
-    ms_img, _ = ev_time(lambda: [tr.sdf_renderer_lod0.render(a, b, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0,
-                                                              perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
-                                                              conditional_volume=vol, conditional_valid_mask_volume=occ,
-                                                              feature_maps=fmaps, color_maps=imgs, w2cs=sample['w2cs'][0],
-                                                              intrinsics=sample['intrinsics'][0], img_wh=[sizeW, sizeH],
-                                                              query_c2w=sample['query_c2w'])
-                                 for a, b in zip(ro.split(CHUNK), rd.split(CHUNK))])
-    t_roof = max(RAY_FLOP / (pk["bf16_tflops"] * 1e12), RAY_GATHER_BYTES / (pk["hbm_gbs"] * 1e9)) * R
-    dom = max(res, key=lambda k: res[k]["ms"])
-    d = res[dom]
-    if "tflops" in d:
-        roof = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": d["tflops"] / pk["bf16_tflops"], "traffic": None,
-                "note": "fp32 FFMA kernel measured against the bf16 tensor peak (SURVEY.md 8(d) row B8); fp32 SIMT peak is ~72 TFLOP/s"}
-    else:
-        roof = {"kernel": dom, "bound": "hbm", "achieved": d["gather_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": d["gather_gbs"] / pk["hbm_gbs"], "traffic": None,
-                "note": "achieved = requested gather bytes of the valid (sample, view) pairs / kernel time"}
-    roof["kernels"] = res
-    roof["raymarch_image_ms"] = ms_img
-    roof["raymarch_frac_of_contract"] = (t_roof * 1e3) / ms_img
-    # informational: reconstruction-only mesh export at R=256 (device part + host copies)
+    def timed(fn):
+        def wrap(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            rec.append((e0, e1))
+            return r
+        return wrap
+    ops_a.gemm, ops_a.bgemm = timed(real_gemm), timed(real_bgemm)
+    unet.use_cuda_graph = False
+    try:
+        unet(x, t, ctx)
+        rec.clear()
+        unet(x, t, ctx)
+        torch.cuda.synchronize()
+        ms_gemm = sum(a.elapsed_time(b) for a, b in rec)
+        n_gemm = len(rec)
+    finally:
+        ops_a.gemm, ops_a.bgemm = real_gemm, real_bgemm
+        unet.use_cuda_graph = True
+    z = torch.randn(4, 4, 32, 32, device=dev)
+    vae.decode(z)
+    ms_dec = float(np.mean([ev_time(lambda: vae.decode(z))[0] for _ in range(3)]))
+    flops = 8 * UNET_FLOP_PER_SAMPLE
+    tf = flops / (ms_gemm * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_f16_tc_kernel (tcgen05.mma kind::f16, all %d GEMMs of one UNet iteration at batch 8)" % n_gemm,
+                "bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
+                "traffic": None, "flops_per_step": flops, "gemm_ms_per_unet_iteration": ms_gemm,
+                "note": "algorithmic FLOPs = 176.3 GFLOP per sample-step x 8 (SURVEY.md 8(d) row A2) / summed CUDA-event time "
+                        "of the GEMM launches of one eager UNet pass"}
+    # ---- reconstruction stages + volume rendering
+    sample = synthetic_sample(dev, n_views=N_VIEWS, H=H, W=W)
+    tr._conditional_features(sample)
+    ms_front, (imgs, fmaps, cond, sizeW, sizeH) = ev_time(lambda: tr._conditional_features(sample))
     tr.base_exp_dir = None
+    tr(sample, mode="export_mesh", resolution=MESH_RES)
     torch.cuda.synchronize()
     w0 = time.perf_counter()
     tr(sample, mode="export_mesh", resolution=MESH_RES)
     torch.cuda.synchronize()
-    return roof, time.perf_counter() - w0
+    s_mesh = time.perf_counter() - w0
+    rays = render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk)
+    stages = {"unet_iteration_ms": ms_unet, "unet_total_s": ms_unet * UNET_ITERS * 1e-3, "vae_decode4_ms": ms_dec,
+              "volume_build_ms": ms_front, "export_mesh_s": s_mesh}
+    return {"roofline": roofline, "stages": stages, "rays": rays}
 
 
-def cpu_baseline(tr, sample, budget_rays=48):
-    """Oracle (CPU port of the reference) on a bounded sample: `budget_rays` rays of the same image against the
-    same (GPU-built) volume and feature maps, all host threads.  A reported baseline, not the target."""
-    from helpers import states_torch
-    from oracle import recon_oracle as O
-    imgs, fmaps, cond, sizeW, sizeH = tr._conditional_features(sample)
-    st = states_torch(0)
-    vol, occ = cond['dense_volume_scale0'].cpu(), cond['valid_mask_volume_scale0'].cpu()
-    sel = torch.linspace(0, N_RAYS - 1, budget_rays).long()
-    ro = sample['rays']['rays_o'][0].reshape(-1, 3).cpu()[sel]
-    rd = sample['rays']['rays_v'][0].reshape(-1, 3).cpu()[sel]
-    near, far = sample['query_near_far'][0, :1].cpu(), sample['query_near_far'][0, 1:].cpu()
-    torch.set_num_threads(host_threads())
-    w0 = time.perf_counter()
-    O.render_rays(ro, rd, near, far, vol, occ, fmaps.cpu(), imgs.cpu(), sample['w2cs'][0].cpu(), sample['intrinsics'][0].cpu(),
-                  sample['query_c2w'].cpu(), st["sdf_network_lod0"], st["rendering_network_lod0"],
-                  st["variance_network_lod0"]["variance"], W=W, H=H)
-    dt = time.perf_counter() - w0
-    return {"value": budget_rays / dt / 1e6, "unit": "M rays/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{budget_rays} rays x (64+64) samples x {N_VIEWS} views of the same image, volume + feature maps prebuilt ({dt:.1f} s)"}
+def render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk):
+    from o2345 import ops
+    from o2345.sparse_sdf_network import channel_last_volume
+    vol, occ = cond['dense_volume_scale0'], cond['valid_mask_volume_scale0']
+    near, far = sample['query_near_far'][0, :1], sample['query_near_far'][0, 1:]
+    ro = ops.cf32(sample['rays']['rays_o'][0].reshape(-1, 3))
+    rd = ops.cf32(sample['rays']['rays_v'][0].reshape(-1, 3))
+
+    def image():
+        outs = []
+        for a, b in zip(ro.split(CHUNK), rd.split(CHUNK)):
+            o = tr.sdf_renderer_lod0.render(a, b, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0,
+                                            perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
+                                            conditional_volume=vol, conditional_valid_mask_volume=occ, feature_maps=fmaps,
+                                            color_maps=imgs, w2cs=sample['w2cs'][0], intrinsics=sample['intrinsics'][0],
+                                            img_wh=[sizeW, sizeH], query_c2w=sample['query_c2w'])
+            outs.append(o)
+        return outs
+    image()
+    ms_img, outs = ev_time(image)
+    o = outs[0]
+    # dominant kernels of the ray march, timed alone on the first chunk
+    vol_cl = channel_last_volume(vol)
+    pack = tr.sdf_network_lod0.sdf_layer.packed()
+    mid = o['mid_z_vals'].contiguous()
+    active = (o['inside_sphere'] > 0).to(torch.uint8).reshape(-1).contiguous()
+    n_act = int(active.sum())
+    src = ops.PointSource.rays(ro[:CHUNK], rd[:CHUNK], mid)
+    f_sdf = lambda: ops.sdf_query(src, vol_cl, pack, active=active, want_grad=True)
+    f_sdf()
+    ms_sdf = float(np.mean([ev_time(f_sdf)[0] for _ in range(3)]))
+    views = tr.sdf_renderer_lod0._source_views(fmaps, imgs, sample['w2cs'][0], sample['intrinsics'][0], [sizeW, sizeH])
+    qc = ops.cf32(sample['query_c2w'].reshape(-1, 4, 4)[0, :3, 3])
+    f_bl = lambda: ops.render_blend(src, active, vol_cl, occ, views, tr.rendering_network_lod0.packed(), query_center=qc)
+    f_bl()
+    ms_bl = float(np.mean([ev_time(f_bl)[0] for _ in range(3)]))
+    pairs = int(f_bl()[1].sum())
+    t_roof = max(RAY_FLOP / (pk["bf16_tflops"] * 1e12), RAY_GATHER_BYTES / (pk["hbm_gbs"] * 1e9)) * N_RAYS
+    return {"metric": "volume-render M rays/sec", "value": N_RAYS / (ms_img * 1e-3) / 1e6, "unit": "M rays/s",
+            "workload": "65536 rays x (64+64) samples x 32 views, fp32, volume + feature maps resident",
+            "image_ms": ms_img, "frac_of_survey_contract": t_roof * 1e3 / ms_img,
+            "kernels_first_chunk": {
+                "sdf_query_kernel<grad>": {"ms": ms_sdf, "tflops": n_act * (FLOP_SDF_FWD + FLOP_SDF_BWD) / (ms_sdf * 1e-3) / 1e12,
+                                           "active_samples": n_act},
+                "render_blend_kernel": {"ms": ms_bl, "valid_pairs": pairs,
+                                        "gather_gbs": (pairs * 960 + n_act * 544) / (ms_bl * 1e-3) / 1e9}}}
 
 
 def host_threads():
-    """Threads for the CPU arm: every core up to 32 (the torch-CPU port stops scaling, and on a 128-thread
-    host gets slower, beyond that; the count actually used is what the JSON reports as `cores`)."""
+    """Threads for the CPU arm: every core up to 32 (the torch-CPU port stops scaling beyond that; the count actually
+    used is what the JSON reports as `cores`)."""
     return max(1, min(os.cpu_count() or 1, 32))
 
 
-def run_reference(args):
-    """--impl reference: the CPU restatement of the reference (oracle/) on the host cores, same metric."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
+def cpu_reference():
+    """The reference's own algorithm on the host cores (oracle/ port, fp32): a bounded sample of every stage of one
+    mesh, extrapolated to the full workload -- 1 UNet iteration at batch 8 (x544), 1 VAE decode of one latent (x40),
+    1 VAE encode (x10), the full 96^3 volume build, and a 48^3 SDF grid (x (256/48)^3)."""
     from helpers import states_torch
     from o2345 import synthetic as S
-    from oracle import recon_oracle as O
+    from oracle import ldm_oracle as LO, recon_oracle as O, vae_oracle as VO
     torch.set_num_threads(host_threads())
-    st = states_torch(0)
-    cams = S.scene_cameras(S.pose_json(60.0), n_src=N_VIEWS, img_wh=(W, H))
-    imgs = torch.from_numpy(S.images(N_VIEWS + 1, H, W, seed=1234))[1:]
     t = lambda x: torch.from_numpy(np.asarray(x)).float()
     w0 = time.perf_counter()
-    fm = O.pyramid_feature_maps(imgs, st["pyramid_feature_network"])
-    cv = O.conditional_volume(fm, t(cams["partial_vol_origin"]), t(cams["affine_mats"]), st["sdf_network_lod0"], VOL,
-                              2.0 / (VOL - 1), H, W)
-    t_vol = time.perf_counter() - w0
-    ro_all, rv_all = S.query_rays(cams["query_intrinsic"], cams["query_c2w"], H, W)
-    n = args.ref_rays
-    times = []
-    for i in range(args.warmup + args.steps):
-        sel = np.linspace(i, N_RAYS - 1 - i, n).astype(np.int64)
+    sd_u = {k: torch.from_numpy(v) for k, v in S.unet_state(0).items()}
+    sd_v = {k: torch.from_numpy(v) for k, v in S.vae_state(10).items()}
+    t_setup = time.perf_counter() - w0
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
         w0 = time.perf_counter()
-        O.render_rays(t(ro_all[sel]), t(rv_all[sel]), t(cams["query_near_far"][:1]), t(cams["query_near_far"][1:]),
-                      cv["dense"], cv["occ"], fm, imgs, t(cams["w2cs"]), t(cams["intrinsics"]), t(cams["query_c2w"])[None],
-                      st["sdf_network_lod0"], st["rendering_network_lod0"], st["variance_network_lod0"]["variance"], W=W, H=H)
-        if i >= args.warmup:
-            times.append(time.perf_counter() - w0)
-    per_ray = float(np.mean(times)) / n
-    step_s = t_vol + per_ray * N_RAYS          # one full step = volume build + all 65536 rays (extrapolated)
-    val = N_RAYS / step_s / 1e6
-    cores = torch.get_num_threads()
-    smp = (f"volume build once ({t_vol:.1f} s, timed) + {n} rays per step extrapolated to 65536 rays "
-           f"({per_ray * 1e3:.1f} ms/ray)")
-    print(json.dumps({"impl": "reference", "metric": "volume-render M rays/sec", "value": val, "unit": "M rays/s",
-                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic", "config": CONFIG,
-                      "cpu_baseline": {"value": val, "unit": "M rays/s", "cores": cores, "kind": "port", "sample": smp},
-                      "e2e": {"value": val, "unit": "M rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        LO.unet_forward(sd_u, torch.randn(8, 8, 32, 32, generator=g), torch.full((8,), 501), torch.randn(8, 1, 768, generator=g))
+        t_unet = time.perf_counter() - w0
+        w0 = time.perf_counter()
+        VO.decode(sd_v, torch.randn(1, 4, 32, 32, generator=g))
+        t_dec = time.perf_counter() - w0
+        w0 = time.perf_counter()
+        VO.encode_moments(sd_v, torch.rand(1, 3, 256, 256, generator=g) * 2 - 1)
+        t_enc = time.perf_counter() - w0
+        st = states_torch(0)
+        cams = S.scene_cameras(S.pose_json(60.0), n_src=N_VIEWS, img_wh=(W, H))
+        imgs = torch.from_numpy(S.images(N_VIEWS + 1, H, W, seed=1234))[1:]
+        w0 = time.perf_counter()
+        fm = O.pyramid_feature_maps(imgs, st["pyramid_feature_network"])
+        cv = O.conditional_volume(fm, t(cams["partial_vol_origin"]), t(cams["affine_mats"]), st["sdf_network_lod0"], VOL,
+                                  2.0 / (VOL - 1), H, W)
+        t_vol = time.perf_counter() - w0
+        w0 = time.perf_counter()
+        O.sdf_grid(cv["dense"], st["sdf_network_lod0"], 48)
+        t_grid = (time.perf_counter() - w0) * (MESH_RES / 48.0) ** 3
+    total = UNET_ITERS * t_unet + 40 * t_dec + 10 * t_enc + t_vol + t_grid
+    return {"value": total, "unit": "s/mesh", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 UNet iteration at batch 8 ({t_unet:.2f} s, x{UNET_ITERS}) + 1 VAE decode ({t_dec:.2f} s, x40) + 1 VAE encode "
+                      f"({t_enc:.2f} s, x10) + full 96^3 volume build ({t_vol:.1f} s) + 48^3 SDF grid scaled to 256^3 ({t_grid:.0f} s); "
+                      f"marching cubes / vertex colours not included; weights generated in {t_setup:.0f} s (untimed)"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference (oracle/) on the host cores, same metric and config."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    cb = cpu_reference()
+    print(json.dumps({"impl": "reference", "metric": "sec/mesh end-to-end (256x256 in)", "value": cb["value"], "unit": "s/mesh",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["value"] * 1e3,
+                      "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": CONFIG, "cpu_baseline": cb,
+                      "e2e": {"value": cb["value"], "unit": "s/mesh", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="o2345", choices=["o2345", "reference"])
-    ap.add_argument("--cpu-rays", type=int, default=48)
-    ap.add_argument("--ref-rays", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

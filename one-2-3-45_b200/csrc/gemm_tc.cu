@@ -120,7 +120,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B
@@ -322,6 +322,9 @@ extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int 
   p.alpha = alpha, p.batched = nh > 0 ? 1 : 0;
   int batch = nh > 0 ? nh * nb : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 64) return launch<64, 6>(ma, mb, p, batch, st);
-  return launch<128, 5>(ma, mb, p, batch, st);
+  // 3 / 4 stages (~97 KB) so that two CTAs share an SM: one CTA's prologue / epilogue overlaps the other's
+  // main loop (r1 ncu launch list: the 5-stage, one-CTA-per-SM variant spent most of a UNet pass in per-CTA
+  // fixed cost).  TMEM: 2 x 128 columns <= 512.
+  if (BN == 64) return launch<64, 4>(ma, mb, p, batch, st);
+  return launch<128, 3>(ma, mb, p, batch, st);
 }

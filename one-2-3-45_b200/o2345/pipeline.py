@@ -112,3 +112,32 @@ def load_sample(folder, device):
     H, W = imgs.shape[2:]
     cams = S.scene_cameras(meta, n_src=32, img_wh=(W, H))
     return _sample_from(cams, imgs, device, H, W)[0]
+
+
+# --------------------------------------------------------------------------------------
+# run.py end to end (reference run.py:79-119): image -> 8 + 32 generated views -> mesh
+# --------------------------------------------------------------------------------------
+def sample_from_views(stage1, stage2, pose, device, pin=False):
+    """The batch dict of BlenderPerView built from in-memory views instead of PNG files."""
+    ids = list(pose["c2ws"].keys())
+    to_f = lambda u8: (u8.astype(np.float32) / 255.0).transpose(2, 0, 1)
+    first = int(ids[0].split(".")[0])
+    imgs = [to_f(stage1[first])] + [to_f(stage2[ids[v].split(".")[0]]) for v in range(8, 40)]
+    imgs = np.stack(imgs).astype(np.float32)
+    H, W = imgs.shape[2:]
+    cams = S.scene_cameras(pose, n_src=32, img_wh=(W, H))
+    return _sample_from(cams, imgs, device, H, W, pin=pin)[0]
+
+
+@torch.no_grad()
+def image_to_mesh(zero123, trainer, input_u8, polar_angle=60, resolution=256, ddim_steps=75, stage2_steps=50, scale=3.0,
+                  exp_dir=None):
+    """`python run.py --img_path X --half_precision` without SAM / elevation estimation: Zero123 stage 1 + stage 2
+    (10 DDIM sampler calls), camera set-up, cost volume, SDF grid, marching cubes, vertex colours.
+    Returns dict(vertices, triangles, colors) as host numpy arrays (and writes mesh.ply when exp_dir is given)."""
+    from .zero123 import generate_views
+    dev = next(trainer.parameters()).device
+    stage1, stage2, pose = generate_views(zero123, input_u8, polar_angle, ddim_steps, stage2_steps, scale, exp_dir, dev)
+    sample = sample_from_views(stage1, stage2, pose, dev)
+    trainer.base_exp_dir = exp_dir
+    return trainer(sample, mode="export_mesh", resolution=resolution)

@@ -26,7 +26,8 @@ def main():
     from o2345.pipeline import build_networks
     dev = torch.device("cuda:0")
     tr = build_networks(dev, vol_dim=bench.VOL, states=S.all_states(0), perturb=0.0)
-    sample, _, _ = bench.build_scene(dev, 1234)
+    from o2345.pipeline import synthetic_sample
+    sample = synthetic_sample(dev, n_views=bench.N_VIEWS, H=bench.H, W=bench.W)
     imgs, fmaps, cond, sizeW, sizeH = tr._conditional_features(sample)
     vol, occ = cond['dense_volume_scale0'], cond['valid_mask_volume_scale0']
     near, far = sample['query_near_far'][0, :1], sample['query_near_far'][0, 1:]
