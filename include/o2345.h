@@ -289,7 +289,8 @@ int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream)
 int o2345_silu(const void* x, int64_t n, void* y, o2345_stream_t stream);
 int o2345_transpose_tokens(const void* x, int B, int N, int C, void* y, o2345_stream_t stream);
 int o2345_timestep_embedding(const float* t, int B, int dim, void* out, o2345_stream_t stream);
-int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, o2345_stream_t stream);
+/* y[b, p, c] += e[b * lde + c] */
+int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, int lde, o2345_stream_t stream);
 int o2345_copy_channels(const void* src, int64_t M, int C, void* dst, int ldd, int off, o2345_stream_t stream);
 int o2345_nchw_f32_to_cl_f16(const float* x, int B, int C, int HW, void* y, int ldy, int off, o2345_stream_t stream);
 int o2345_cl_f16_to_nchw_f32(const void* x, int B, int C, int HW, int ldx, float* y, o2345_stream_t stream);

@@ -169,12 +169,12 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 }
 
 // y[b, p, c] += e[b, c]   (ResBlock: h + emb_out[..., None, None], openaimodel.py:271)
-__global__ void add_channel_bias_kernel(__half* __restrict__ y, const __half* __restrict__ e, int HW, int C, int64_t total) {
+__global__ void add_channel_bias_kernel(__half* __restrict__ y, const __half* __restrict__ e, int HW, int C, int lde, int64_t total) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
   int64_t b = i / ((int64_t)HW * C);
-  y[i] = __float2half_rn(__half2float(y[i]) + __half2float(e[b * C + c]));
+  y[i] = __float2half_rn(__half2float(y[i]) + __half2float(e[b * lde + c]));
 }
 
 // dst[:, off:off+C] = src  (channel concat on channel-last rows)
@@ -291,10 +291,10 @@ extern "C" int o2345_timestep_embedding(const float* t, int B, int dim, void* ou
   return O2345_OK;
 }
 
-extern "C" int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, o2345_stream_t stream) {
+extern "C" int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, int lde, o2345_stream_t stream) {
   O2345_CHECK_ARG(y && e, "null pointer");
   int64_t total = (int64_t)B * HW * C;
-  add_channel_bias_kernel<<<cdiv(total, 256), 256, 0, ST>>>((__half*)y, (const __half*)e, HW, C, total);
+  add_channel_bias_kernel<<<cdiv(total, 256), 256, 0, ST>>>((__half*)y, (const __half*)e, HW, C, lde, total);
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -82,7 +82,7 @@ _SIGS = {
     "o2345_silu": (C.c_int, [c_fp, c_i64, c_fp, c_fp]),
     "o2345_transpose_tokens": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "o2345_timestep_embedding": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp]),
-    "o2345_add_channel_bias": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp]),
+    "o2345_add_channel_bias": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "o2345_copy_channels": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, C.c_int, C.c_int, c_fp]),
     "o2345_nchw_f32_to_cl_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, C.c_int, c_fp]),
     "o2345_cl_f16_to_nchw_f32": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),

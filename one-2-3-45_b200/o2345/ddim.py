@@ -92,11 +92,19 @@ class DDIMSampler(object):
             scale = 1.0
         else:
             x_in, t_in = torch.cat([x] * 2), torch.cat([t] * 2)
-            if isinstance(c, dict):
-                c_in = {k: ([torch.cat([unconditional_conditioning[k][i], c[k][i]]) for i in range(len(c[k]))]
-                            if isinstance(c[k], list) else torch.cat([unconditional_conditioning[k], c[k]])) for k in c}
+            # the conditioning does not change between the steps of one sampling call: build [uncond | cond] once and
+            # hand the model the SAME tensor objects every step (lets it reuse context-only work, e.g. the UNet's
+            # single-token cross-attention)
+            cache = getattr(self, "_cin", None)
+            if cache is not None and cache[0] is c and cache[1] is unconditional_conditioning:
+                c_in = cache[2]
             else:
-                c_in = torch.cat([unconditional_conditioning, c])
+                if isinstance(c, dict):
+                    c_in = {k: ([torch.cat([unconditional_conditioning[k][i], c[k][i]]) for i in range(len(c[k]))]
+                                if isinstance(c[k], list) else torch.cat([unconditional_conditioning[k], c[k]])) for k in c}
+                else:
+                    c_in = torch.cat([unconditional_conditioning, c])
+                self._cin = (c, unconditional_conditioning, c_in)
             e2 = self.model.apply_model(x_in, t_in, c_in).float().contiguous()
             scale = unconditional_guidance_scale
         noise = torch.randn(x.shape, device=x.device) * temperature     # noise_like(), reference util.py:264-267

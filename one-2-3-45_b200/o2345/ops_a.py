@@ -93,7 +93,8 @@ def timestep_embedding(t, dim):
 
 
 def add_channel_bias(y, e, B, HW, Cc):
-    L.call("o2345_add_channel_bias", _v(y), _v(e), B, HW, Cc, _stream())
+    """y[b, p, c] += e[b, c]; e may be a column slice of a wider [B, ld] matrix."""
+    L.call("o2345_add_channel_bias", _v(y), _v(e), B, HW, Cc, e.stride(0), _stream())
     return y
 
 

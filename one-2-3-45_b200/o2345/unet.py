@@ -176,6 +176,7 @@ class UNetModel(nn.Module):
         self._packed = None
         self.use_cuda_graph = True
         self._graphs = {}
+        self._ctx_ref, self._ctx_ver, self._cross_out = None, None, {}
 
     # ------------------------------------------------------------------ executor
     def _pk(self):
@@ -194,11 +195,24 @@ class UNetModel(nn.Module):
         w, b = pk.conv(conv)
         return A.gemm(a, w, bias=b, residual=residual), Ho, Wo
 
-    def _resblock(self, pk, blk, x, B, H, W, emb_act):
+    def _emb_pack(self, pk):
+        """All 22 ResBlock `emb_layers` Linears as ONE [sum Cout, 1280] GEMM per iteration (they share the input)."""
+        if "emb_all" not in pk.w:
+            blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+            ws, bs, off, o = [], [], {}, 0
+            for b in blocks:
+                w, bias = pk.linear(b.emb_layers[1])
+                ws.append(w), bs.append(bias)
+                off[id(b)] = o
+                o += w.shape[0]
+            pk.w["emb_all"] = (torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous(), off)
+        return pk.w["emb_all"]
+
+    def _resblock(self, pk, blk, x, B, H, W, emb_all):
         C, Co = blk.channels, blk.out_channels
         h, _, _ = self._conv3(pk, x, B, H, W, C, blk.in_layers[2], gn=blk.in_layers[0], act=True)
-        we, be = pk.linear(blk.emb_layers[1])
-        A.add_channel_bias(h, A.gemm(emb_act, we, bias=be), B, H * W, Co)
+        off = self._emb_pack(pk)[2][id(blk)]
+        A.add_channel_bias(h, emb_all[:, off:off + Co], B, H * W, Co)
         if isinstance(blk.skip_connection, nn.Identity):
             skip = x
         else:
@@ -221,14 +235,31 @@ class UNetModel(nn.Module):
         wo, bo = pk.linear(attn.to_out[0])
         return A.gemm(o, wo, bias=bo, residual=residual)
 
-    def _cross_attention(self, pk, blk, h, ctx16, B, N, C):
+    def _ensure_context(self, context):
+        """Single-token cross-attention depends on the context only: out = to_out(to_v(ctx)), constant over the image and
+        over every DDIM step of a sampling call.  It is computed once per context TENSOR OBJECT (identity + version; a
+        strong reference is kept so the address cannot be recycled) into static buffers the captured graph reads."""
+        B, T = context.shape[0], context.shape[1]
+        if T != 1 or (context is self._ctx_ref and context._version == self._ctx_ver):
+            return
+        pk = self._pk()
+        ctx16 = context.reshape(B, -1).to(_f16).contiguous()
+        for st in (m for m in self.modules() if isinstance(m, SpatialTransformer)):
+            attn = st.transformer_blocks[0].attn2
+            wv, _ = pk.linear(attn.to_v)
+            wo, bo = pk.linear(attn.to_out[0])
+            key = (id(st), B)
+            if key not in self._cross_out:
+                self._cross_out[key] = torch.empty(B, wo.shape[0], dtype=_f16, device=context.device)
+            A.gemm(A.gemm(ctx16, wv), wo, bias=bo, out=self._cross_out[key])
+        self._ctx_ref, self._ctx_ver = context, context._version
+
+    def _cross_attention(self, pk, st, blk, h, ctx16, B, N, C):
         attn = blk.attn2
         T = ctx16.shape[0] // B
         wo, bo = pk.linear(attn.to_out[0])
-        if T == 1:  # one key: softmax == 1, output = to_out(to_v(ctx)) for every query token
-            wv, _ = pk.linear(attn.to_v)
-            o = A.gemm(A.gemm(ctx16, wv), wo, bias=bo)                      # [B, C]
-            return A.add_channel_bias(h, o, B, N, C)
+        if T == 1:  # one key: softmax == 1, output = to_out(to_v(ctx)) for every query token (see _ensure_context)
+            return A.add_channel_bias(h, self._cross_out[(id(st), B)], B, N, C)
         H, d = attn.heads, attn.dim_head
         xn = A.layernorm(h, *pk.norm(blk.norm2), eps=blk.norm2.eps)
         q = A.gemm(xn, pk.linear(attn.to_q)[0])
@@ -254,7 +285,7 @@ class UNetModel(nn.Module):
         h = A.gemm(a, wi, bias=bi)
         blk = st.transformer_blocks[0]
         h = self._attention(pk, blk.attn1, A.layernorm(h, *pk.norm(blk.norm1), eps=blk.norm1.eps), B, N, C, h)
-        h = self._cross_attention(pk, blk, h, ctx16, B, N, C)
+        h = self._cross_attention(pk, st, blk, h, ctx16, B, N, C)
         w1, b1 = pk.linear(blk.ff.net[0].proj)
         w2, b2 = pk.linear(blk.ff.net[2])
         g = A.geglu(A.gemm(A.layernorm(h, *pk.norm(blk.norm3), eps=blk.norm3.eps), w1, bias=b1))
@@ -285,6 +316,7 @@ class UNetModel(nn.Module):
         CUDA graph and replayed (the pass is launch-bound from Python: 18 ms eager vs the device time of the graph);
         the returned tensor is the graph's static output buffer and is overwritten by the next call."""
         assert y is None, "the Zero123 UNet is not class-conditional"
+        self._ensure_context(context)
         if not (self.use_cuda_graph and x.is_cuda) or torch.cuda.is_current_stream_capturing():
             return self._forward_impl(x, timesteps, context)
         from . import _lib
@@ -315,7 +347,8 @@ class UNetModel(nn.Module):
         w0, b0 = pk.linear(self.time_embed[0])
         w2, b2 = pk.linear(self.time_embed[2])
         emb = A.gemm(A.gemm(t_emb, w0, bias=b0, act=1), w2, bias=b2)
-        emb_act = A.silu(emb)                                               # every ResBlock starts emb_layers with SiLU
+        wa, ba, _ = self._emb_pack(pk)
+        emb_act = A.gemm(A.silu(emb), wa, bias=ba)                          # [B, sum Cout]: emb_layers of every ResBlock
         ctx16 = context.reshape(-1, context.shape[-1]).to(_f16).contiguous()
         hs = []
         for seq in self.input_blocks:

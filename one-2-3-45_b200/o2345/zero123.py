@@ -70,7 +70,7 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         xc = torch.cat([x_noisy] + cond["c_concat"], dim=1)
-        cc = torch.cat(cond["c_crossattn"], 1)
+        cc = cond["c_crossattn"][0] if len(cond["c_crossattn"]) == 1 else torch.cat(cond["c_crossattn"], 1)
         return self.model.diffusion_model(xc, t, context=cc)
 
     @torch.no_grad()
