@@ -284,6 +284,11 @@ int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, 
 int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,
                          o2345_stream_t stream);
 int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream);
+/* Fused multi-head self-attention (ldm/modules/attention.py:170-193): out[b, n, h*d + j] = softmax(q k^T * scale) v.
+ * q, k, v: fp16 [B*N, >= H*d] views with a common row stride ld (e.g. column blocks of a fused qkv projection);
+ * d in {40, 80, 160}; scores stay on chip (mma.sync m16n8k16, fp32 online softmax). */
+int o2345_attention_f16(const void* q, const void* k, const void* v, int B, int N, int H, int d, int ld, void* out,
+                        int ldo, float scale, o2345_stream_t stream);
 /* y[M,I] = x[:, :I] * gelu(x[:, I:2I]) */
 int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream);
 int o2345_silu(const void* x, int64_t n, void* y, o2345_stream_t stream);

@@ -1,0 +1,173 @@
+// Fused multi-head self-attention for the UNet's spatial transformers: softmax(Q K^T * scale) V in one
+// kernel, scores never leave the SM.  Replaces reference ldm/modules/attention.py:170-193, which materialises the
+// [(b h), N, N] score tensor (134 MB per layer at N = 1024) three times; the r1 three-kernel version here (batched tcgen05
+// GEMM -> softmax -> batched GEMM) spent 0.43 ms per layer in 4096 one-k-block CTAs for QK^T alone.
+//
+// Head dims are 40 / 80 / 160 and sequences 16..1024 tokens: far too small per (batch, head) to fill a 128-row tcgen05
+// tile pipeline, so this kernel uses warp-level mma.sync.m16n8k16 (fp16 in, fp32 accumulate) in the FlashAttention-2
+// arrangement: one CTA = 4 warps = 64 queries of one (b, h); K / V stream through shared memory in 64-key tiles (V stored
+// transposed so that both B operands are 32-bit shared loads); online softmax in fp32 registers with exp2; the S
+// accumulator fragments are re-used in place as the A fragments of the P V product.  The arithmetic is softmax-bound
+// (N^2 exps per head), not tensor-bound, at these sizes.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace o2345 {
+namespace {
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float x, float y) {
+  __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int QT = 64, KT = 64;  // queries per CTA, keys per tile
+
+template <int D, int DP>  // head dim and its padding to a multiple of 16
+__global__ void __launch_bounds__(128)
+attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v, int N, int H, int ld,
+                 __half* __restrict__ out, int ldo, float scale_log2) {
+  constexpr int LDQ = DP + 8, LDV = KT + 8, KS = DP / 16, NO = DP / 8;
+  extern __shared__ __align__(16) __half smem_h[];
+  __half* sQ = smem_h;
+  __half* sK = sQ + QT * LDQ;
+  __half* sVt = sK + KT * LDQ;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * QT;
+  const int64_t base = (int64_t)b * N * ld + (int64_t)h * D;
+  constexpr int CH = D / 8;  // 16-byte chunks per row
+
+  for (int i = tid; i < QT * LDQ / 8; i += 128) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = tid; i < QT * CH; i += 128) {
+    int r = i / CH, c = i % CH;
+    if (q0 + r < N) *reinterpret_cast<uint4*>(sQ + r * LDQ + 8 * c) = *reinterpret_cast<const uint4*>(q + base + (int64_t)(q0 + r) * ld + 8 * c);
+  }
+  __syncthreads();
+  uint32_t qa[KS][4];
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) {
+    const __half* p0 = sQ + (16 * warp + g) * LDQ + 16 * kk + 2 * t;
+    qa[kk][0] = *reinterpret_cast<const uint32_t*>(p0);
+    qa[kk][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * LDQ);
+    qa[kk][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+    qa[kk][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * LDQ + 8);
+  }
+  float o[NO][4];
+#pragma unroll
+  for (int n = 0; n < NO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+
+  for (int k0 = 0; k0 < N; k0 += KT) {
+    __syncthreads();  // previous tile fully consumed
+    for (int i = tid; i < KT * LDQ / 8; i += 128) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < DP * LDV / 8; i += 128) reinterpret_cast<uint4*>(sVt)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = tid; i < KT * CH; i += 128) {
+      int r = i / CH, c = i % CH;
+      if (k0 + r < N) {
+        *reinterpret_cast<uint4*>(sK + r * LDQ + 8 * c) = *reinterpret_cast<const uint4*>(k + base + (int64_t)(k0 + r) * ld + 8 * c);
+        uint4 vv = *reinterpret_cast<const uint4*>(v + base + (int64_t)(k0 + r) * ld + 8 * c);
+        const __half* hv = reinterpret_cast<const __half*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sVt[(8 * c + e) * LDV + r] = hv[e];
+      }
+    }
+    __syncthreads();
+    // ---- S = Q K^T for this warp's 16 queries x 64 keys
+    float s[KT / 8][4];
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const __half* pk = sK + (8 * j + g) * LDQ + 16 * kk + 2 * t;
+        mma16816(s[j], qa[kk], *reinterpret_cast<const uint32_t*>(pk), *reinterpret_cast<const uint32_t*>(pk + 8));
+      }
+    }
+    // ---- online softmax (rows g and g+8 of this warp's tile), base-2 exponent with the scale folded in
+    float mx0 = -1e30f, mx1 = -1e30f;
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) {
+      int key = k0 + 8 * j + 2 * t;
+      s[j][0] = key < N ? s[j][0] * scale_log2 : -1e30f;
+      s[j][1] = key + 1 < N ? s[j][1] * scale_log2 : -1e30f;
+      s[j][2] = key < N ? s[j][2] * scale_log2 : -1e30f;
+      s[j][3] = key + 1 < N ? s[j][3] * scale_log2 : -1e30f;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    m0 = mn0, m1 = mn1;
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - mn0), s[j][1] = exp2f(s[j][1] - mn0);
+      s[j][2] = exp2f(s[j][2] - mn1), s[j][3] = exp2f(s[j][3] - mn1);
+      r0 += s[j][0] + s[j][1], r1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * a0 + r0, l1 = l1 * a1 + r1;
+#pragma unroll
+    for (int n = 0; n < NO; ++n) o[n][0] *= a0, o[n][1] *= a0, o[n][2] *= a1, o[n][3] *= a1;
+    // ---- O += P V : the S fragments are exactly the A fragments of the next product
+#pragma unroll
+    for (int kk = 0; kk < KT / 16; ++kk) {
+      uint32_t pa[4] = {pack2(s[2 * kk][0], s[2 * kk][1]), pack2(s[2 * kk][2], s[2 * kk][3]),
+                        pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+#pragma unroll
+      for (int n = 0; n < NO; ++n) {
+        const __half* pv = sVt + (8 * n + g) * LDV + 16 * kk + 2 * t;
+        mma16816(o[n], pa, *reinterpret_cast<const uint32_t*>(pv), *reinterpret_cast<const uint32_t*>(pv + 8));
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1), l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  float i0 = 1.f / l0, i1 = 1.f / l1;
+  int row0 = q0 + 16 * warp + g, row1 = row0 + 8;
+#pragma unroll
+  for (int n = 0; n < NO; ++n) {
+    int col = 8 * n + 2 * t;
+    if (col < D) {
+      if (row0 < N) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * N + row0) * ldo + h * D + col) = pack2(o[n][0] * i0, o[n][1] * i0);
+      if (row1 < N) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * N + row1) * ldo + h * D + col) = pack2(o[n][2] * i1, o[n][3] * i1);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace o2345
+
+using namespace o2345;
+
+extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, int B, int N, int H, int d, int ld, void* out,
+                                   int ldo, float scale, o2345_stream_t stream) {
+  O2345_CHECK_ARG(q && k && v && out, "null pointer");
+  O2345_CHECK_ARG(B > 0 && N > 0 && H > 0 && (ld % 8) == 0 && (ldo % 2) == 0, "bad sizes");
+  O2345_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0, "q/k/v must be 16-byte aligned");
+  dim3 grid(cdiv(N, QT), B * H);
+  float sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half *qh = (const __half*)q, *kh = (const __half*)k, *vh = (const __half*)v;
+  auto smem = [](int dp) { return (size_t)((QT + KT) * (dp + 8) + dp * (KT + 8)) * sizeof(__half); };
+  static bool attr = false;
+  if (!attr) {
+    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(160)));
+    attr = true;
+  }
+  if (d == 40) attention_kernel<40, 48><<<grid, 128, smem(48), st>>>(qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2);
+  else if (d == 80) attention_kernel<80, 80><<<grid, 128, smem(80), st>>>(qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2);
+  else if (d == 160) attention_kernel<160, 160><<<grid, 128, smem(160), st>>>(qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2);
+  else { set_error("o2345_attention_f16: head dim %d not built (40 / 80 / 160)", d); return O2345_EUNSUPPORTED; }
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}

@@ -78,6 +78,8 @@ _SIGS = {
                                         C.c_int, c_fp, c_fp, C.c_int, c_fp, c_fp]),
     "o2345_layernorm_rows": (C.c_int, [c_fp, c_i64, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp]),
     "o2345_softmax_rows": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
+    "o2345_attention_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,
+                                      C.c_float, c_fp]),
     "o2345_geglu": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
     "o2345_silu": (C.c_int, [c_fp, c_i64, c_fp, c_fp]),
     "o2345_transpose_tokens": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),

@@ -131,3 +131,12 @@ def silu(x):
     y = torch.empty_like(x)
     L.call("o2345_silu", _v(x), x.numel(), _v(y), _stream())
     return y
+
+
+def attention(q, k, v, B, N, H, d, out=None):
+    """softmax(q k^T / sqrt(d)) v per (batch, head); q/k/v are [B*N, >=H*d] views sharing one row stride."""
+    assert q.stride(0) == k.stride(0) == v.stride(0) and q.stride(1) == 1
+    if out is None:
+        out = torch.empty(B * N, H * d, dtype=_f16, device=q.device)
+    L.call("o2345_attention_f16", _v(q), _v(k), _v(v), B, N, H, d, q.stride(0), _v(out), out.stride(0), float(d) ** -0.5, _stream())
+    return out

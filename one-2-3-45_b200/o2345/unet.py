@@ -225,6 +225,10 @@ class UNetModel(nn.Module):
         """Self-attention on layer-normed tokens xn [B*N, C]; returns to_out(...) + residual."""
         H, d = attn.heads, attn.dim_head
         qkv = A.gemm(xn, pk.qkv(attn))                                   # [B*N, 3C]
+        if d in (40, 80, 160):                                            # fused kernel: scores never leave the SM
+            o = A.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, N, H, d)
+            wo, bo = pk.linear(attn.to_out[0])
+            return A.gemm(o, wo, bias=bo, residual=residual)
         s = torch.empty(B * H, N, N, dtype=_f16, device=xn.device)
         q, k = qkv[:, :C], qkv[:, C:2 * C]
         A.bgemm(q, k, s, H, B, (d, N * 3 * C), (d, N * 3 * C), (N * N, H * N * N), N, N, d, 3 * C, 3 * C, N, alpha=d ** -0.5)
