@@ -267,6 +267,13 @@ int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, i
                    int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const float* bias, const void* residual,
                    int act, float alpha, int out_f32, o2345_stream_t stream);
 
+/* Implicit-GEMM 3x3 convolution, stride 1, zero padding 1 (nn.Conv2d(C, N, 3, padding=1) of the UNet ResBlocks and the
+ * VAE ResnetBlocks): x channel-last [B,H,W,C] fp16, weight [N, 9*C] fp16 in (ky,kx,c) order, out [B*H*W, N] (row stride
+ * ldc).  No im2col buffer exists: the nine shifted windows are fetched by 4-D TMA boxes whose out-of-bounds zero fill is
+ * the padding.  W must divide 128 or be a multiple of 128; C a multiple of 8.  Epilogue as o2345_gemm_f16. */
+int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
+                      const float* bias, const void* residual, int act, int out_f32, o2345_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Path A glue (rows A1, A3, A4, A6): channel-last fp16 activations [B, H*W, C]; fp32 statistics.
  * GroupNorm32 / SiLU / conv patch gather: ldm/modules/diffusionmodules/openaimodel.py:92-161,256-276,

@@ -111,6 +111,10 @@ struct GemmParams {
   int act;                     // 0 none, 1 SiLU, 2 GELU(erf)
   float alpha;                 // scale applied to the accumulator before bias
   int batched;                 // 4-D tensor maps (K, rows, h, b)
+  // implicit 3x3 convolution (stride 1, zero padding 1): A is the channel-last activation [B, H, W, C] seen through a
+  // 4-D tensor map (C, W, H, B); an output tile of 128 consecutive pixels is a box (64 ch, tw, th, tb), and kernel tap
+  // (ky, kx) is the same box shifted by (kx-1, ky-1) -- TMA's out-of-bounds zero fill IS the convolution padding.
+  int conv, cC, cH, cW, cblocks;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -135,7 +139,7 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, bz = blockIdx.z;
-  const int nk = (p.K + BK - 1) / BK;
+  const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -161,7 +165,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-        if (p.batched) {
+        if (p.conv) {
+          const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
+          const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
+          tma_load_4d(sA + s * A_BYTES, &tmA, full + s, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+          tma_load_2d(sB + s * B_BYTES, &tmB, full + s, tap * p.cC + c0, n0);
+        } else if (p.batched) {
           tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * BK, m0, bz % p.nh, bz / p.nh);
           tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * BK, n0, bz % p.nh, bz / p.nh);
         } else {
@@ -299,6 +308,41 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int 
 
 using namespace o2345;
 
+extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
+                                 const float* bias, const void* residual, int act, int out_f32, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && weight && out, "null pointer");
+  O2345_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0 && N > 0, "bad sizes (C must be a multiple of 8)");
+  O2345_CHECK_ARG((128 % W) == 0 || (W % 128) == 0, "image width must divide or be a multiple of the 128-pixel tile");
+  O2345_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)weight % 16) == 0, "operands must be 16-byte aligned");
+  O2345_CHECK_ARG(act >= 0 && act <= 2, "unknown activation");
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return O2345_ECUDA; }
+  const int tw = W >= 128 ? 128 : W;
+  const int th = W >= 128 ? 1 : (128 / W < H ? 128 / W : H);
+  const int tb = 128 / (tw * th);
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (conv activation) failed with %d", (int)r); return O2345_ECUDA; }
+  }
+  const int BN = N <= 64 ? 64 : 128;
+  int rc = make_map(&mb, weight, N, 9 * (int64_t)C, 9 * (int64_t)C, 0, 0, 0, 0, BN);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = B * H * W, p.N = N, p.K = 9 * C, p.ldc = ldc, p.nh = 1, p.stride_c_h = 0, p.stride_c_b = 0;
+  p.bias = bias, p.residual = reinterpret_cast<const __half*>(residual), p.C = out, p.out_f32 = out_f32, p.act = act;
+  p.alpha = 1.f, p.batched = 0, p.conv = 1, p.cC = C, p.cH = H, p.cW = W, p.cblocks = (C + BK - 1) / BK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 64) return launch<64, 4>(ma, mb, p, 0, st);
+  return launch<128, 3>(ma, mb, p, 0, st);
+}
+
 extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
                               int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
                               int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const float* bias,
@@ -320,6 +364,7 @@ extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int 
   p.M = M, p.N = N, p.K = K, p.ldc = ldc, p.nh = nh > 0 ? nh : 1, p.stride_c_h = stride_c_h, p.stride_c_b = stride_c_b;
   p.bias = bias, p.residual = reinterpret_cast<const __half*>(residual), p.C = C, p.out_f32 = out_f32, p.act = act;
   p.alpha = alpha, p.batched = nh > 0 ? 1 : 0;
+  p.conv = 0, p.cC = p.cH = p.cW = p.cblocks = 0;
   int batch = nh > 0 ? nh * nb : 0;
   cudaStream_t st = (cudaStream_t)stream;
   // 3 / 4 stages (~97 KB) so that two CTAs share an SM: one CTA's prologue / epilogue overlaps the other's

@@ -140,3 +140,17 @@ def attention(q, k, v, B, N, H, d, out=None):
         out = torch.empty(B * N, H * d, dtype=_f16, device=q.device)
     L.call("o2345_attention_f16", _v(q), _v(k), _v(v), B, N, H, d, q.stride(0), _v(out), out.stride(0), float(d) ** -0.5, _stream())
     return out
+
+
+def conv3x3(x, B, H, W, C, weight, bias=None, residual=None, act=0, out_dtype=_f16):
+    """Implicit-GEMM 3x3 convolution (stride 1, pad 1) of a channel-last activation x [B*H*W, C]; weight [N, 9*C] in
+    (ky, kx, c) order.  No im2col buffer: TMA fetches the nine shifted windows, zero-filling outside the image."""
+    N = weight.shape[0]
+    out = torch.empty(B * H * W, N, dtype=out_dtype, device=x.device)
+    L.call("o2345_conv3x3_f16", _v(x), B, H, W, C, _v(weight), N, _v(out), out.stride(0), _p(bias, _f32), _v(residual),
+           int(act), int(out_dtype == _f32), _stream())
+    return out
+
+
+def conv3x3_supported(W, C):
+    return C % 8 == 0 and C >= 64 and (128 % W == 0 or W % 128 == 0)

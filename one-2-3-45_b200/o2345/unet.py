@@ -191,8 +191,12 @@ class UNetModel(nn.Module):
             mean, rstd = A.groupnorm_stats(x, B, H * W, C, 32, gn.eps)
             gamma, beta = pk.norm(gn)
             g = (mean, rstd, 32, gamma, beta)
-        a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, 3, stride, up, g, act)
         w, b = pk.conv(conv)
+        if stride == 1 and not up and A.conv3x3_supported(W, C):
+            # implicit GEMM: normalise once ([M, C], not 9x) and let TMA fetch the nine shifted windows
+            a = x if g is None else A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, act)[0]
+            return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual), H, W
+        a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, 3, stride, up, g, act)
         return A.gemm(a, w, bias=b, residual=residual), Ho, Wo
 
     def _emb_pack(self, pk):
