@@ -132,8 +132,11 @@ class AutoencoderKL(nn.Module):
         if gn is not None:
             mean, rstd = A.groupnorm_stats(x, B, H * W, C, 32, gn.eps)
             g = (mean, rstd, 32, *pk.norm(gn))
-        a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, ksize, stride, up, g, gn is not None and ksize == 3, pad_lo=pad_lo)
         w, b = pk.conv(conv)
+        if ksize == 3 and stride == 1 and not up and pad_lo < 0 and A.conv3x3_supported(W, C):
+            a = x if g is None else A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, True)[0]
+            return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual), H, W
+        a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, ksize, stride, up, g, gn is not None and ksize == 3, pad_lo=pad_lo)
         return A.gemm(a, w, bias=b, residual=residual), Ho, Wo
 
     def _res(self, pk, blk, x, B, H, W):

@@ -71,3 +71,19 @@ def test_batched_gemm_heads_inside_a_token_tensor():
     ops_a.bgemm(p, vt, o, H, B, (N * N, H * N * N), (d * N, Cc * N), (d, N * Cc), N, d, N, N, N, Cc)
     want_o = torch.einsum("bhij,bjhd->bihd", p.float().view(B, H, N, N), v.float().view(B, N, H, d)).reshape(B, N, Cc)
     assert (o.float() - want_o).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(8, 32, 32, 320, 320), (8, 16, 16, 640, 640), (8, 8, 8, 1280, 1280), (8, 4, 4, 1280, 1280),
+                                       (2, 64, 64, 512, 512), (1, 256, 256, 128, 128), (3, 8, 8, 72, 40), (1, 128, 128, 256, 3)])
+def test_implicit_conv3x3_matches_conv2d(B, H, W, C, N):
+    """The TMA shifted-window convolution against F.conv2d (fp32) on the same fp16 operands."""
+    from o2345 import ops_a
+    g = torch.Generator(device="cuda").manual_seed(H + C)
+    x = (torch.randn(B, H, W, C, device="cuda", generator=g) * 0.5).half()
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) * (2.0 / (9 * C)) ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    wk = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = ops_a.conv3x3(x.view(-1, C), B, H, W, C, wk, bias=bias, out_dtype=torch.float32)
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    err = (out - want).abs().max().item()
+    assert err < 5e-3, err
