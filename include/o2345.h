@@ -265,14 +265,18 @@ int o2345_ray_composite(const float* rays_d, int64_t R, int S, const float* mid_
 int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
                    int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const float* bias, const void* residual,
-                   int act, float alpha, int out_f32, o2345_stream_t stream);
+                   int act, float alpha, int out_f32, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
+/* splitk_ws (optional, may be NULL): fp32 scratch of ws_floats >= M*N elements that is ALL ZERO on entry; when the output
+ * tiles alone cannot fill the GPU the K range is split over several CTAs per tile that accumulate into it, and a finalize
+ * kernel applies the epilogue and leaves it zeroed again. */
 
 /* Implicit-GEMM 3x3 convolution, stride 1, zero padding 1 (nn.Conv2d(C, N, 3, padding=1) of the UNet ResBlocks and the
  * VAE ResnetBlocks): x channel-last [B,H,W,C] fp16, weight [N, 9*C] fp16 in (ky,kx,c) order, out [B*H*W, N] (row stride
  * ldc).  No im2col buffer exists: the nine shifted windows are fetched by 4-D TMA boxes whose out-of-bounds zero fill is
  * the padding.  W must divide 128 or be a multiple of 128; C a multiple of 8.  Epilogue as o2345_gemm_f16. */
 int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
-                      const float* bias, const void* residual, int act, int out_f32, o2345_stream_t stream);
+                      const float* bias, const void* residual, int act, int out_f32, float* splitk_ws, int64_t ws_floats,
+                      o2345_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Path A glue (rows A1, A3, A4, A6): channel-last fp16 activations [B, H*W, C]; fp32 statistics.

