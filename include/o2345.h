@@ -256,16 +256,29 @@ int o2345_ray_composite(const float* rays_d, int64_t R, int S, const float* mid_
  * attention einsums of the Zero123 UNet and VAE:
  *          ldm/modules/diffusionmodules/openaimodel.py:745-777, ldm/modules/attention.py:170-193,
  *          ldm/modules/diffusionmodules/model.py:535-568.
- * C[b] = act(alpha * A[b] . B[b]^T + bias) + residual[b];  A [M,K] (row stride lda), B [N,K] (row stride
- * ldb), fp16, K contiguous; C and residual [M,N] (row stride ldc), C fp16 or fp32.  nh = 0: plain GEMM;
+ * C[b] = act(alpha * A[b] . B[b]^T + bias + rowbias) + residual[b];  A [M,K] (row stride lda), B [N,K] (row
+ * stride ldb), fp16, K contiguous; C and residual [M,N] (row stride ldc), C fp16 or fp32.  nh = 0: plain GEMM;
  * nh > 0: nh * nb independent products, operand z = b * nh + h lives at ptr + h * stride_*_h + b * stride_*_b
- * (e.g. heads inside a [B, N, H*d] tensor).  act: 0 none, 1 SiLU, 2 GELU.
- * lda, ldb and the A/B batch strides must be multiples of 8 elements (TMA: 16-byte strides).
+ * (e.g. heads inside a [B, N, H*d] tensor).  lda, ldb and the A/B batch strides must be multiples of 8 elements
+ * (TMA: 16-byte strides).
  * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* bias;     /* [N] fp32 or NULL */
+  const void* residual;  /* fp16 [M, ldc] or NULL, added after the activation (ResBlock / attention skip) */
+  const void* rowbias;   /* fp16 or NULL: element [(row / rows_per_group) * rowbias_ld + col] is added before the
+                            activation (the ResBlock's per-image emb_layers output, openaimodel.py:266-273) */
+  int64_t rowbias_ld;
+  int rows_per_group;
+  int act;               /* 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU (attention.py:37-44): the N columns come in chunks of
+                            32 = 16 values followed by their 16 gates, C gets N/2 columns value * gelu(gate) */
+  float alpha;           /* scale on the accumulator */
+  int out_f32;           /* C is fp32 instead of fp16 */
+} o2345_epilogue;
+
 int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
-                   int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const float* bias, const void* residual,
-                   int act, float alpha, int out_f32, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
+                   int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const o2345_epilogue* ep /* NULL: plain */,
+                   float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
 /* splitk_ws (optional, may be NULL): fp32 scratch of ws_floats >= M*N elements that is ALL ZERO on entry; when the output
  * tiles alone cannot fill the GPU the K range is split over several CTAs per tile that accumulate into it, and a finalize
  * kernel applies the epilogue and leaves it zeroed again. */
@@ -275,8 +288,7 @@ int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, i
  * ldc).  No im2col buffer exists: the nine shifted windows are fetched by 4-D TMA boxes whose out-of-bounds zero fill is
  * the padding.  W must divide 128 or be a multiple of 128; C a multiple of 8.  Epilogue as o2345_gemm_f16. */
 int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
-                      const float* bias, const void* residual, int act, int out_f32, float* splitk_ws, int64_t ws_floats,
-                      o2345_stream_t stream);
+                      const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Path A glue (rows A1, A3, A4, A6): channel-last fp16 activations [B, H*W, C]; fp32 statistics.
@@ -284,14 +296,17 @@ int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* wei
  *   ldm/modules/diffusionmodules/util.py:214-216; LayerNorm / softmax / GEGLU: ldm/modules/attention.py:37-64,
  *   170-193,214-218; timestep embedding: util.py:151-171; CFG + DDIM update: ldm/models/diffusion/ddim.py:196-243.
  * ------------------------------------------------------------------------------------------ */
-int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, float* mean, float* rstd,
-                          o2345_stream_t stream);
-/* out [B*Ho*Wo, k*k*C] (column order ky,kx,c) = patches of f(x), f = GroupNorm(+SiLU if act) when mean != NULL.
+/* GroupNorm statistics folded into a per-(image, channel) affine: GroupNorm(x)[b, p, c] = x * scale[b, c] + shift[b, c]
+ * (scale = rstd * gamma, shift = beta - mean * rstd * gamma; gamma / beta may be NULL).  x [B, HW, C] fp16, C a multiple
+ * of 8.  scratch: o2345_groupnorm_scratch_floats(B, G) fp32 words, ALL ZERO on entry and left zeroed. */
+int64_t o2345_groupnorm_scratch_floats(int B, int G);
+int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta,
+                          float* scratch, float* scale, float* shift, o2345_stream_t stream);
+/* out [B*Ho*Wo, k*k*C] (column order ky,kx,c) = patches of f(x), f = x * scale + shift (+SiLU if act) when scale != NULL.
  * upsample != 0: nearest x2 replication of x before the convolution.  Zero padding k/2 on the high side and
  * pad_lo on the low side (pad_lo < 0: k/2; pad_lo = 0 reproduces the VAE encoder's F.pad(x, (0,1,0,1))). */
 int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample, int pad_lo,
-                          const float* mean, const float* rstd, int G, const float* gamma, const float* beta, int act,
-                          void* out, o2345_stream_t stream);
+                          const float* scale, const float* shift, int act, void* out, o2345_stream_t stream);
 int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,
                          o2345_stream_t stream);
 int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream);

@@ -3,7 +3,7 @@
 // DDIM update are computed in fp32, matching the reference's autocast policy (GroupNorm32 / LayerNorm /
 // softmax in fp32: ldm/modules/diffusionmodules/util.py:214-216, SURVEY.md section 8 header).
 //
-//   groupnorm_stats      per (batch, group) mean / rstd                     openaimodel.py:256-276 (GroupNorm32)
+//   groupnorm_stats      per (image, group) statistics -> per (image, channel) scale / shift   openaimodel.py:256-276 (GroupNorm32)
 //   norm_act_im2col      GroupNorm apply (+SiLU) fused with the 3x3 / 1x1 patch gather (optionally behind a
 //                        nearest x2 up-sampling or with stride 2) -> the K-major A operand of the conv GEMM
 //   layernorm_rows       attention.py:214-218
@@ -22,39 +22,76 @@ namespace {
 
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
 
-// one CTA per (batch, group): x [B, HW, C] fp16, G groups of C/G channels
+// GroupNorm statistics folded into a per-(image, channel) affine: y = x * scale[b, c] + shift[b, c] with
+// scale = rstd * gamma, shift = beta - mean * rstd * gamma.  x [B, HW, C] fp16 channel-last.
+// grid (chunks, B): a CTA reads a slab of pixels with 16-byte loads (thread = fixed 8-channel slot, so the partial sums
+// stay in registers), folds them into per-group shared-memory sums, adds those to the global scratch, and the LAST CTA
+// of each image (ticket counter) turns the totals into scale / shift and leaves the scratch zeroed for the next call.
 __global__ void groupnorm_stats_kernel(const __half* __restrict__ x, int HW, int C, int G, float eps,
-                                       float* __restrict__ mean, float* __restrict__ rstd) {
-  const int b = blockIdx.x / G, g = blockIdx.x % G;
-  const int cg = C / G;
-  const __half* base = x + (int64_t)b * HW * C + g * cg;
-  float s = 0.f, q = 0.f;
-  for (int i = threadIdx.x; i < HW * cg; i += blockDim.x) {
-    int p = i / cg, c = i - p * cg;
-    float v = __half2float(base[(int64_t)p * C + c]);
-    s += v, q = fmaf(v, v, q);
-  }
-  __shared__ float ss[32], sq[32];
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
-  if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = s, sq[threadIdx.x >> 5] = q;
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* __restrict__ scratch, int B, int P,
+                                       float* __restrict__ scale, float* __restrict__ shift) {
+  extern __shared__ float gsm[];           // [2 G] sums, then [2 G] mean / rstd
+  __shared__ int is_last;
+  const int b = blockIdx.y, c8n = C >> 3, cg = C / G;
+  const int slot = threadIdx.x % c8n, prow = threadIdx.x / c8n, rows = blockDim.x / c8n;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) gsm[i] = 0.f;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    int nw = blockDim.x >> 5;
-    s = threadIdx.x < nw ? ss[threadIdx.x] : 0.f, q = threadIdx.x < nw ? sq[threadIdx.x] : 0.f;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (threadIdx.x == 0) {
-      float n = (float)HW * cg, m = s / n;
-      float var = fmaxf(q / n - m * m, 0.f);
-      mean[blockIdx.x] = m, rstd[blockIdx.x] = rsqrtf(var + eps);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f, q[e] = 0.f;
+  const int p0 = blockIdx.x * P, p1 = min(HW, p0 + P);
+  const __half* base = x + (int64_t)b * HW * C + slot * 8;
+  if (prow < rows) {
+    for (int pix = p0 + prow; pix < p1; pix += rows) {
+      uint4 v = *reinterpret_cast<const uint4*>(base + (int64_t)pix * C);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h[e]);
+        s[2 * e] += f.x, q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
+        s[2 * e + 1] += f.y, q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
+      }
     }
+    int g = (slot * 8) / cg;
+    float rs = 0.f, rq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int ge = (slot * 8 + e) / cg;
+      if (ge != g) { atomicAdd(gsm + 2 * g, rs), atomicAdd(gsm + 2 * g + 1, rq), rs = rq = 0.f, g = ge; }
+      rs += s[e], rq += q[e];
+    }
+    atomicAdd(gsm + 2 * g, rs), atomicAdd(gsm + 2 * g + 1, rq);
+  }
+  __syncthreads();
+  float* tot = scratch + (int64_t)b * 2 * G;
+  int* ticket = reinterpret_cast<int*>(scratch + (int64_t)B * 2 * G) + b;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(tot + i, gsm[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float n = (float)HW * cg, m = __ldcg(tot + 2 * g) / n;
+    float var = fmaxf(__ldcg(tot + 2 * g + 1) / n - m * m, 0.f);
+    gsm[2 * g] = m, gsm[2 * g + 1] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) tot[i] = 0.f;
+  if (threadIdx.x == 0) *ticket = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m = gsm[2 * (c / cg)], r = gsm[2 * (c / cg) + 1];
+    float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    scale[(int64_t)b * C + c] = r * ga, shift[(int64_t)b * C + c] = be - m * r * ga;
   }
 }
 
-// out[(b, oy, ox), (ky, kx, c)] = f(in[b, iy, ix, c]);  f = optional GroupNorm(+SiLU).  KS in {1,3}; `up` doubles the
-// input grid by nearest-neighbour replication before the convolution; zero padding of KS/2.
+// out[(b, oy, ox), (ky, kx, c)] = f(in[b, iy, ix, c]);  f = optional per-(image, channel) affine (GroupNorm) (+SiLU).
+// KS in {1,3}; `up` doubles the input grid by nearest-neighbour replication before the convolution; zero padding.
 __global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int KS, int stride, int up,
-                                       const float* __restrict__ mean, const float* __restrict__ rstd, int G,
-                                       const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                       const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                        __half* __restrict__ out, int Ho, int Wo, int pad) {
   const int c8 = C >> 3;  // 8 channels (16 bytes) per thread
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,16 +108,19 @@ __global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int 
   if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
     int sy = up ? iy >> 1 : iy, sx = up ? ix >> 1 : ix;
     uint4 v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + sy) * W + sx) * C + cc * 8);
-    if (mean) {
-      const __half* h = reinterpret_cast<const __half*>(&v);
-      __half r[8];
-      int cg = C / G;
+    if (scale) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      const float4* sc = reinterpret_cast<const float4*>(scale + (int64_t)b * C + cc * 8);
+      const float4* sh = reinterpret_cast<const float4*>(shift + (int64_t)b * C + cc * 8);
+      float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), t0 = __ldg(sh), t1 = __ldg(sh + 1);
+      float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      __half2 r[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        int c = cc * 8 + e, g = c / cg;
-        float f = (__half2float(h[e]) - mean[b * G + g]) * rstd[b * G + g] * gamma[c] + beta[c];
-        if (act) f = silu(f);
-        r[e] = __float2half_rn(f);
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h[e]);
+        f.x = fmaf(f.x, sv[2 * e], tv[2 * e]), f.y = fmaf(f.y, sv[2 * e + 1], tv[2 * e + 1]);
+        if (act) f.x = silu(f.x), f.y = silu(f.y);
+        r[e] = __floats2half2_rn(f.x, f.y);
       }
       o = *reinterpret_cast<uint4*>(r);
     } else {
@@ -128,12 +168,21 @@ __global__ void softmax_rows_kernel(const __half* __restrict__ s, int64_t rows, 
 }
 
 __global__ void geglu_kernel(const __half* __restrict__ x, int64_t M, int I, __half* __restrict__ y) {
+  const int i8 = I >> 3;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * I) return;
-  int64_t r = i / I;
-  int c = (int)(i - r * I);
-  float a = __half2float(x[r * 2 * I + c]), g = __half2float(x[r * 2 * I + I + c]);
-  y[i] = __float2half_rn(a * (0.5f * g * (1.f + erff(g * 0.70710678118654752f))));
+  if (i >= M * i8) return;
+  int64_t r = i / i8;
+  int c = (int)(i - r * i8) * 8;
+  uint4 va = *reinterpret_cast<const uint4*>(x + r * 2 * I + c), vg = *reinterpret_cast<const uint4*>(x + r * 2 * I + I + c);
+  const __half* a = reinterpret_cast<const __half*>(&va);
+  const __half* g = reinterpret_cast<const __half*>(&vg);
+  __half o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float gf = __half2float(g[e]);
+    o[e] = __float2half_rn(__half2float(a[e]) * (0.5f * gf * (1.f + erff(gf * 0.70710678118654752f))));
+  }
+  *reinterpret_cast<uint4*>(y + r * I + c) = *reinterpret_cast<uint4*>(o);
 }
 
 __global__ void silu_kernel(const __half* __restrict__ x, int64_t n, __half* __restrict__ y) {
@@ -225,25 +274,36 @@ __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float*
 using namespace o2345;
 #define ST ((cudaStream_t)stream)
 
-extern "C" int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, float* mean, float* rstd,
-                                     o2345_stream_t stream) {
-  O2345_CHECK_ARG(x && mean && rstd && C % G == 0, "bad arguments");
-  groupnorm_stats_kernel<<<B * G, 256, 0, ST>>>((const __half*)x, HW, C, G, eps, mean, rstd);
+extern "C" int64_t o2345_groupnorm_scratch_floats(int B, int G) { return (int64_t)B * 2 * G + B; }
+
+extern "C" int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, const float* gamma,
+                                     const float* beta, float* scratch, float* scale, float* shift, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && scratch && scale && shift && B > 0 && HW > 0 && G > 0 && C % G == 0, "bad arguments");
+  O2345_CHECK_ARG((C % 8) == 0 && C / 8 <= 1024 && ((uintptr_t)x % 16) == 0, "C must be a multiple of 8 (<= 8192), x 16-byte aligned");
+  const int c8n = C / 8;
+  const int rows = c8n >= 256 ? 1 : 256 / c8n;
+  const int threads = c8n * rows;
+  int chunks = cdiv(2 * sm_count(), B);
+  if (chunks > HW / (2 * rows)) chunks = HW / (2 * rows);
+  if (chunks < 1) chunks = 1;
+  const int P = cdiv(HW, chunks);
+  chunks = cdiv(HW, P);
+  groupnorm_stats_kernel<<<dim3(chunks, B), threads, 4 * G * sizeof(float), ST>>>((const __half*)x, HW, C, G, eps, gamma, beta,
+                                                                                  scratch, B, P, scale, shift);
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample, int pad_lo,
-                                     const float* mean, const float* rstd, int G, const float* gamma, const float* beta,
-                                     int act, void* out, o2345_stream_t stream) {
+                                     const float* scale, const float* shift, int act, void* out, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && out && (C % 8) == 0 && (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "bad arguments");
-  O2345_CHECK_ARG(!mean || (rstd && gamma && beta && G > 0 && C % G == 0), "incomplete GroupNorm arguments");
+  O2345_CHECK_ARG(!scale == !shift, "scale and shift come together");
   int Hin = upsample ? 2 * H : H, Win = upsample ? 2 * W : W;
   int pad_hi = ksize / 2, pad = pad_lo < 0 ? ksize / 2 : pad_lo;   // pad_lo = 0: the VAE's (0,1,0,1) down-sampling pad
   int Ho = (Hin + pad + pad_hi - ksize) / stride + 1, Wo = (Win + pad + pad_hi - ksize) / stride + 1;
   int64_t total = (int64_t)B * Ho * Wo * ksize * ksize * (C / 8);
-  norm_act_im2col_kernel<<<cdiv(total, 256), 256, 0, ST>>>((const __half*)x, B, H, W, C, ksize, stride, upsample, mean, rstd, G,
-                                                           gamma, beta, act, (__half*)out, Ho, Wo, pad);
+  norm_act_im2col_kernel<<<cdiv(total, 256), 256, 0, ST>>>((const __half*)x, B, H, W, C, ksize, stride, upsample, scale, shift,
+                                                           act, (__half*)out, Ho, Wo, pad);
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
@@ -264,8 +324,8 @@ extern "C" int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o
 }
 
 extern "C" int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream) {
-  O2345_CHECK_ARG(x && y, "null pointer");
-  geglu_kernel<<<cdiv(M * I, 256), 256, 0, ST>>>((const __half*)x, M, I, (__half*)y);
+  O2345_CHECK_ARG(x && y && (I % 8) == 0, "null pointer / I must be a multiple of 8");
+  geglu_kernel<<<cdiv(M * (I / 8), 256), 256, 0, ST>>>((const __half*)x, M, I, (__half*)y);
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -29,6 +29,11 @@ class Views(C.Structure):
                 ("centers", c_fp), ("sizeW", C.c_float), ("sizeH", C.c_float)]
 
 
+class Epilogue(C.Structure):
+    _fields_ = [("bias", c_fp), ("residual", c_fp), ("rowbias", c_fp), ("rowbias_ld", c_i64), ("rows_per_group", C.c_int),
+                ("act", C.c_int), ("alpha", C.c_float), ("out_f32", C.c_int)]
+
+
 PTS_EXPLICIT, PTS_LATTICE, PTS_RAYS = 0, 1, 2
 SDF_PACK_FLOATS = 39 * 128 + 128 + 2 * (144 * 128 + 128) + 128 * 144 + 128 * 48
 RNET_PACK_FLOATS = 19664
@@ -72,13 +77,14 @@ _SIGS = {
     "o2345_render_blend": (C.c_int, [C.POINTER(Points), c_i64, c_fp, c_fp, c_fp, C.c_int, C.POINTER(Views),
                                      C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "o2345_gemm_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int,
-                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_fp, c_fp, C.c_int, C.c_float, C.c_int, c_fp, c_i64,
-                                 c_fp]),
-    "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64, c_fp, c_fp, C.c_int,
-                                    C.c_int, c_fp, c_i64, c_fp]),
-    "o2345_groupnorm_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp]),
+                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
+    "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64,
+                                    C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
+    "o2345_groupnorm_scratch_floats": (c_i64, [C.c_int, C.c_int]),
+    "o2345_groupnorm_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                        c_fp]),
     "o2345_norm_act_im2col": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp,
-                                        C.c_int, c_fp, c_fp, C.c_int, c_fp, c_fp]),
+                                        C.c_int, c_fp, c_fp]),
     "o2345_layernorm_rows": (C.c_int, [c_fp, c_i64, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp]),
     "o2345_softmax_rows": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
     "o2345_attention_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,

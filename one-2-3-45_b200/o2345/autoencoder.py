@@ -128,10 +128,7 @@ class AutoencoderKL(nn.Module):
 
     @staticmethod
     def _conv(pk, x, B, H, W, C, conv, gn=None, stride=1, up=False, residual=None, pad_lo=-1, ksize=3):
-        g = None
-        if gn is not None:
-            mean, rstd = A.groupnorm_stats(x, B, H * W, C, 32, gn.eps)
-            g = (mean, rstd, 32, *pk.norm(gn))
+        g = None if gn is None else A.groupnorm_stats(x, B, H * W, C, 32, gn.eps, *pk.norm(gn))
         w, b = pk.conv(conv)
         if ksize == 3 and stride == 1 and not up and pad_lo < 0 and A.conv3x3_supported(W, C):
             a = x if g is None else A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, True)[0]
@@ -151,8 +148,8 @@ class AutoencoderKL(nn.Module):
 
     def _attn(self, pk, at, x, B, H, W):
         C, N = at.in_channels, H * W
-        mean, rstd = A.groupnorm_stats(x, B, N, C, 32, at.norm.eps)
-        xn, _, _ = A.norm_act_im2col(x, B, H, W, C, 1, 1, False, (mean, rstd, 32, *pk.norm(at.norm)), False)
+        g = A.groupnorm_stats(x, B, N, C, 32, at.norm.eps, *pk.norm(at.norm))
+        xn, _, _ = A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, False)
         q = A.gemm(xn, *pk.conv(at.q)[:1], bias=pk.conv(at.q)[1])
         k = A.gemm(xn, *pk.conv(at.k)[:1], bias=pk.conv(at.k)[1])
         v = A.gemm(xn, *pk.conv(at.v)[:1], bias=pk.conv(at.v)[1])

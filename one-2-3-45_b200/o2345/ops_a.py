@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import ctypes as C_
 
 import torch
 
@@ -27,46 +28,80 @@ def _splitk_ws(dev):
     return _WS[k]
 
 
-def gemm(a, b, bias=None, residual=None, act=0, alpha=1.0, out_dtype=_f16, out=None):
-    """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + residual.  a, b fp16 with contiguous K; rows may be strided."""
+def _epilogue(bias=None, residual=None, rowbias=None, rows_per_group=1, act=0, alpha=1.0, out_f32=False):
+    """o2345_epilogue; the tensors must stay alive until the call returns (they are arguments of the caller)."""
+    if rowbias is not None:
+        assert rowbias.dtype == _f16 and rowbias.stride(-1) == 1
+    return L.Epilogue(bias=_p(bias, _f32), residual=None if residual is None else residual.data_ptr(),
+                      rowbias=None if rowbias is None else rowbias.data_ptr(),
+                      rowbias_ld=0 if rowbias is None else rowbias.stride(0), rows_per_group=int(rows_per_group),
+                      act=int(act), alpha=float(alpha), out_f32=int(out_f32))
+
+
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU = 0, 1, 2, 3
+
+
+def gemm(a, b, bias=None, residual=None, act=0, alpha=1.0, out_dtype=_f16, out=None, rowbias=None, rows_per_group=1):
+    """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias + rowbias[row // rows_per_group]) + residual.  a, b fp16 with
+    contiguous K; rows may be strided.  act = ACT_GEGLU: b's rows are interleaved 16 values / 16 gates (geglu_pack) and
+    out has N/2 columns."""
     assert a.dtype == _f16 and b.dtype == _f16 and a.stride(-1) == 1 and b.stride(-1) == 1
     M, K = a.shape
     N = b.shape[0]
     assert b.shape[1] == K, (a.shape, b.shape)
     if out is None:
-        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+        out = torch.empty(M, N // 2 if act == ACT_GEGLU else N, dtype=out_dtype, device=a.device)
     assert out.stride(-1) == 1
     if residual is not None:
         assert residual.dtype == _f16 and residual.stride(0) == out.stride(0) and residual.stride(-1) == 1
+    ep = _epilogue(bias, residual, rowbias, rows_per_group, act, alpha, out.dtype == _f32)
     L.call("o2345_gemm_f16", _v(a), _v(b), _v(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), 0, 0, 0, 0, 0, 0, 0, 0,
-           _p(bias, _f32), _v(residual), int(act), float(alpha), int(out.dtype == _f32), _v(_splitk_ws(a.device)), WS_FLOATS,
-           _stream())
+           C.byref(ep), _v(_splitk_ws(a.device)), WS_FLOATS, _stream())
     return out
+
+
+def geglu_pack(w, bias):
+    """Reorders the rows of a GEGLU projection ([2I, K]: I values then I gates) into chunks of 16 values + their 16 gates,
+    the column order the ACT_GEGLU epilogue expects."""
+    I = w.shape[0] // 2
+    assert I % 16 == 0
+    idx = torch.arange(I, device=w.device).reshape(-1, 16)
+    perm = torch.cat([idx, idx + I], 1).reshape(-1)
+    return w[perm].contiguous(), None if bias is None else bias[perm].contiguous()
 
 
 def bgemm(a, b, out, nh, nb, sa, sb, sc, M, N, K, lda, ldb, ldc, alpha=1.0):
     """nh*nb products; sa/sb/sc = (stride_h, stride_b) element offsets of the operand for batch z = b*nh + h."""
+    ep = _epilogue(alpha=alpha, out_f32=out.dtype == _f32)
     L.call("o2345_gemm_f16", _v(a), _v(b), _v(out), M, N, K, lda, ldb, ldc, nh, nb, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1],
-           None, None, 0, float(alpha), int(out.dtype == _f32), None, 0, _stream())
+           C.byref(ep), None, 0, _stream())
     return out
 
 
-def groupnorm_stats(x, B, HW, C, G=32, eps=1e-5):
-    mean = torch.empty(B * G, dtype=_f32, device=x.device)
-    rstd = torch.empty_like(mean)
-    L.call("o2345_groupnorm_stats", _v(x), B, HW, C, G, float(eps), _v(mean), _v(rstd), _stream())
-    return mean, rstd
+_GN_SCRATCH = {}
+
+
+def groupnorm_stats(x, B, HW, C, G=32, eps=1e-5, gamma=None, beta=None):
+    """GroupNorm as a per-(image, channel) affine: returns (scale, shift) fp32 [B, C] with GN(x) = x * scale + shift."""
+    k = (str(x.device), B, G)
+    if k not in _GN_SCRATCH:
+        _GN_SCRATCH[k] = torch.zeros(int(L.load().o2345_groupnorm_scratch_floats(B, G)), dtype=_f32, device=x.device)
+    scale = torch.empty(B, C, dtype=_f32, device=x.device)
+    shift = torch.empty_like(scale)
+    L.call("o2345_groupnorm_stats", _v(x), B, HW, C, G, float(eps), _p(gamma, _f32), _p(beta, _f32), _v(_GN_SCRATCH[k]),
+           _v(scale), _v(shift), _stream())
+    return scale, shift
 
 
 def norm_act_im2col(x, B, H, W, C, ksize=3, stride=1, upsample=False, gn=None, act=False, pad_lo=-1):
-    """gn = (mean, rstd, G, gamma, beta) or None.  Returns ([B*Ho*Wo, k*k*C] fp16, Ho, Wo)."""
+    """gn = (scale, shift) from groupnorm_stats or None.  Returns ([B*Ho*Wo, k*k*C] fp16, Ho, Wo)."""
     Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
     pad_hi = ksize // 2
     pad = pad_hi if pad_lo < 0 else pad_lo
     Ho, Wo = (Hin + pad + pad_hi - ksize) // stride + 1, (Win + pad + pad_hi - ksize) // stride + 1
     out = torch.empty(B * Ho * Wo, ksize * ksize * C, dtype=_f16, device=x.device)
-    mean, rstd, G, gamma, beta = gn if gn is not None else (None, None, 0, None, None)
-    L.call("o2345_norm_act_im2col", _v(x), B, H, W, C, ksize, stride, int(upsample), int(pad_lo), _v(mean), _v(rstd), G, _v(gamma), _v(beta),
+    scale, shift = gn if gn is not None else (None, None)
+    L.call("o2345_norm_act_im2col", _v(x), B, H, W, C, ksize, stride, int(upsample), int(pad_lo), _v(scale), _v(shift),
            int(act), _v(out), _stream())
     return out, Ho, Wo
 
@@ -155,13 +190,15 @@ def attention(q, k, v, B, N, H, d, out=None):
     return out
 
 
-def conv3x3(x, B, H, W, C, weight, bias=None, residual=None, act=0, out_dtype=_f16):
+def conv3x3(x, B, H, W, C, weight, bias=None, residual=None, act=0, out_dtype=_f16, rowbias=None):
     """Implicit-GEMM 3x3 convolution (stride 1, pad 1) of a channel-last activation x [B*H*W, C]; weight [N, 9*C] in
-    (ky, kx, c) order.  No im2col buffer: TMA fetches the nine shifted windows, zero-filling outside the image."""
+    (ky, kx, c) order.  No im2col buffer: TMA fetches the nine shifted windows, zero-filling outside the image.
+    rowbias [B, >=N] fp16: per-image channel bias (the ResBlock's timestep embedding)."""
     N = weight.shape[0]
     out = torch.empty(B * H * W, N, dtype=out_dtype, device=x.device)
-    L.call("o2345_conv3x3_f16", _v(x), B, H, W, C, _v(weight), N, _v(out), out.stride(0), _p(bias, _f32), _v(residual),
-           int(act), int(out_dtype == _f32), _v(_splitk_ws(x.device)), WS_FLOATS, _stream())
+    ep = _epilogue(bias, residual, rowbias, H * W, act, 1.0, out_dtype == _f32)
+    L.call("o2345_conv3x3_f16", _v(x), B, H, W, C, _v(weight), N, _v(out), out.stride(0), C_.byref(ep),
+           _v(_splitk_ws(x.device)), WS_FLOATS, _stream())
     return out
 
 

@@ -121,6 +121,12 @@ class _Packed:
                          None if m.bias is None else m.bias.detach().to(_f32).contiguous())
         return self.w[k]
 
+    def geglu(self, m):
+        k = ("geglu", id(m))
+        if k not in self.w:
+            self.w[k] = A.geglu_pack(*self.linear(m))
+        return self.w[k]
+
     def qkv(self, attn):
         k = ("qkv", id(attn))
         if k not in self.w:
@@ -185,19 +191,15 @@ class UNetModel(nn.Module):
             self._packed = _Packed(self)
         return self._packed
 
-    def _conv3(self, pk, x, B, H, W, C, conv, gn=None, act=False, stride=1, up=False, residual=None):
-        g = None
-        if gn is not None:
-            mean, rstd = A.groupnorm_stats(x, B, H * W, C, 32, gn.eps)
-            gamma, beta = pk.norm(gn)
-            g = (mean, rstd, 32, gamma, beta)
+    def _conv3(self, pk, x, B, H, W, C, conv, gn=None, act=False, stride=1, up=False, residual=None, rowbias=None):
+        g = None if gn is None else A.groupnorm_stats(x, B, H * W, C, 32, gn.eps, *pk.norm(gn))
         w, b = pk.conv(conv)
         if stride == 1 and not up and A.conv3x3_supported(W, C):
             # implicit GEMM: normalise once ([M, C], not 9x) and let TMA fetch the nine shifted windows
             a = x if g is None else A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, act)[0]
-            return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual), H, W
+            return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual, rowbias=rowbias), H, W
         a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, 3, stride, up, g, act)
-        return A.gemm(a, w, bias=b, residual=residual), Ho, Wo
+        return A.gemm(a, w, bias=b, residual=residual, rowbias=rowbias, rows_per_group=Ho * Wo), Ho, Wo
 
     def _emb_pack(self, pk):
         """All 22 ResBlock `emb_layers` Linears as ONE [sum Cout, 1280] GEMM per iteration (they share the input)."""
@@ -214,9 +216,10 @@ class UNetModel(nn.Module):
 
     def _resblock(self, pk, blk, x, B, H, W, emb_all):
         C, Co = blk.channels, blk.out_channels
-        h, _, _ = self._conv3(pk, x, B, H, W, C, blk.in_layers[2], gn=blk.in_layers[0], act=True)
         off = self._emb_pack(pk)[2][id(blk)]
-        A.add_channel_bias(h, emb_all[:, off:off + Co], B, H * W, Co)
+        # h + emb_out[..., None, None] (openaimodel.py:271) rides in the conv epilogue as a per-image channel bias
+        h, _, _ = self._conv3(pk, x, B, H, W, C, blk.in_layers[2], gn=blk.in_layers[0], act=True,
+                              rowbias=emb_all[:, off:off + Co])
         if isinstance(blk.skip_connection, nn.Identity):
             skip = x
         else:
@@ -225,14 +228,14 @@ class UNetModel(nn.Module):
         out, _, _ = self._conv3(pk, h, B, H, W, Co, blk.out_layers[3], gn=blk.out_layers[0], act=True, residual=skip)
         return out, Co
 
-    def _attention(self, pk, attn, xn, B, N, C, residual):
-        """Self-attention on layer-normed tokens xn [B*N, C]; returns to_out(...) + residual."""
+    def _attention(self, pk, attn, xn, B, N, C, residual, rowbias=None):
+        """Self-attention on layer-normed tokens xn [B*N, C]; returns to_out(...) + residual (+ rowbias[image])."""
         H, d = attn.heads, attn.dim_head
         qkv = A.gemm(xn, pk.qkv(attn))                                   # [B*N, 3C]
         if d in (40, 80, 160):                                            # fused kernel: scores never leave the SM
             o = A.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, N, H, d)
             wo, bo = pk.linear(attn.to_out[0])
-            return A.gemm(o, wo, bias=bo, residual=residual)
+            return A.gemm(o, wo, bias=bo, residual=residual, rowbias=rowbias, rows_per_group=N)
         s = torch.empty(B * H, N, N, dtype=_f16, device=xn.device)
         q, k = qkv[:, :C], qkv[:, C:2 * C]
         A.bgemm(q, k, s, H, B, (d, N * 3 * C), (d, N * 3 * C), (N * N, H * N * N), N, N, d, 3 * C, 3 * C, N, alpha=d ** -0.5)
@@ -241,7 +244,7 @@ class UNetModel(nn.Module):
         o = torch.empty(B * N, C, dtype=_f16, device=xn.device)
         A.bgemm(p, vt, o, H, B, (N * N, H * N * N), (d * N, C * N), (d, N * C), N, d, N, N, N, C)
         wo, bo = pk.linear(attn.to_out[0])
-        return A.gemm(o, wo, bias=bo, residual=residual)
+        return A.gemm(o, wo, bias=bo, residual=residual, rowbias=rowbias, rows_per_group=N)
 
     def _ensure_context(self, context):
         """Single-token cross-attention depends on the context only: out = to_out(to_v(ctx)), constant over the image and
@@ -287,17 +290,23 @@ class UNetModel(nn.Module):
 
     def _transformer(self, pk, st, x, B, H, W, C, ctx16):
         N = H * W
-        mean, rstd = A.groupnorm_stats(x, B, N, C, 32, st.norm.eps)
-        a, _, _ = A.norm_act_im2col(x, B, H, W, C, 1, 1, False, (mean, rstd, 32, *pk.norm(st.norm)), False)
+        g = A.groupnorm_stats(x, B, N, C, 32, st.norm.eps, *pk.norm(st.norm))
+        a, _, _ = A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, False)
         wi, bi = pk.conv(st.proj_in)
         h = A.gemm(a, wi, bias=bi)
         blk = st.transformer_blocks[0]
-        h = self._attention(pk, blk.attn1, A.layernorm(h, *pk.norm(blk.norm1), eps=blk.norm1.eps), B, N, C, h)
-        h = self._cross_attention(pk, st, blk, h, ctx16, B, N, C)
-        w1, b1 = pk.linear(blk.ff.net[0].proj)
+        xn = A.layernorm(h, *pk.norm(blk.norm1), eps=blk.norm1.eps)
+        if ctx16.shape[0] == B and (id(st), B) in self._cross_out:
+            # one context token: attn2(h) = to_out(to_v(ctx)) is a per-image constant (see _ensure_context), so
+            # h + attn1(...) + attn2(...) is ONE epilogue: residual h, row-group bias cross_out[image]
+            h = self._attention(pk, blk.attn1, xn, B, N, C, h, rowbias=self._cross_out[(id(st), B)])
+        else:
+            h = self._attention(pk, blk.attn1, xn, B, N, C, h)
+            h = self._cross_attention(pk, st, blk, h, ctx16, B, N, C)
+        w1, b1 = pk.geglu(blk.ff.net[0].proj)        # GEGLU gate applied in the GEMM epilogue: [M, 4C], not [M, 8C], leaves the SM
         w2, b2 = pk.linear(blk.ff.net[2])
-        g = A.geglu(A.gemm(A.layernorm(h, *pk.norm(blk.norm3), eps=blk.norm3.eps), w1, bias=b1))
-        h = A.gemm(g, w2, bias=b2, residual=h)
+        gg = A.gemm(A.layernorm(h, *pk.norm(blk.norm3), eps=blk.norm3.eps), w1, bias=b1, act=A.ACT_GEGLU)
+        h = A.gemm(gg, w2, bias=b2, residual=h)
         wo, bo = pk.conv(st.proj_out)
         return A.gemm(h, wo, bias=bo, residual=x)
 

@@ -87,3 +87,71 @@ def test_implicit_conv3x3_matches_conv2d(B, H, W, C, N):
     want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
     err = (out - want).abs().max().item()
     assert err < 5e-3, err
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 2560, 320), (2048, 640, 5760), (512, 10240, 1280), (128, 1280, 11520), (8, 20160, 1280),
+                                   (8192, 960, 320), (2048, 1920, 640), (4096, 512, 1152), (1000, 256, 192), (300, 192, 72),
+                                   (257, 160, 64), (129, 3840, 1280)])
+def test_pair_kernel_shapes(M, N, K):
+    """Every tile width of the CTA-pair kernel (160 / 256 / 128), M tails inside the second CTA, split-K shapes."""
+    from o2345 import ops_a
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) * 0.5).half()
+    out = ops_a.gemm(a, b, out_dtype=torch.float32)
+    again = ops_a.gemm(a, b, out_dtype=torch.float32)        # the split-K workspace must come back zeroed
+    want = ref(a, b)
+    assert (out - want).abs().max().item() <= 2e-3 * (K ** 0.5)
+    assert (again - want).abs().max().item() <= 2e-3 * (K ** 0.5)
+
+
+def test_rowbias_and_geglu_epilogues():
+    from o2345 import ops_a
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Bn, HW, K, N = 4, 96, 320, 640
+    a = (torch.randn(Bn * HW, K, device="cuda", generator=g) * 0.3).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) * 0.3).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(Bn * HW, N, device="cuda", generator=g).half()
+    emb = torch.randn(Bn, 3 * N, device="cuda", generator=g).half()
+    rb = emb[:, N:2 * N]                                       # a column block of a wider matrix, as emb_all is
+    out = ops_a.gemm(a, b, bias=bias, residual=res, act=1, rowbias=rb, rows_per_group=HW)
+    want = torch.nn.functional.silu(a.float() @ b.float().t() + bias + rb.float().repeat_interleave(HW, 0)) + res.float()
+    assert (out.float() - want).abs().max().item() < 2e-2
+    # GEGLU: value * gelu(gate) with the projection rows interleaved by geglu_pack
+    I = N // 2
+    wp, bp = ops_a.geglu_pack(b, bias)
+    out = ops_a.gemm(a, wp, bias=bp, act=ops_a.ACT_GEGLU)
+    y = a.float() @ b.float().t() + bias
+    want = y[:, :I] * torch.nn.functional.gelu(y[:, I:])
+    assert out.shape == (Bn * HW, I)
+    assert (out.float() - want).abs().max().item() < 2e-2
+    assert (ops_a.geglu((y.half())).float() - (y.half().float()[:, :I] * torch.nn.functional.gelu(y.half().float()[:, I:]))).abs().max() < 2e-2
+
+
+def test_conv_rowbias_split_k():
+    """ResBlock first conv: per-image embedding bias in the epilogue, on a shape that takes the split-K route."""
+    from o2345 import ops_a
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, H, W, C, N = 8, 8, 8, 1280, 1280
+    x = (torch.randn(B, H, W, C, device="cuda", generator=g) * 0.5).half()
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) * (2.0 / (9 * C)) ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    emb = torch.randn(B, N, device="cuda", generator=g).half()
+    wk = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = ops_a.conv3x3(x.view(-1, C), B, H, W, C, wk, bias=bias, rowbias=emb, out_dtype=torch.float32)
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + emb.float()[:, :, None, None]
+    assert (out - want.permute(0, 2, 3, 1).reshape(-1, N)).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("B,HW,C", [(8, 1024, 320), (8, 256, 1920), (8, 16, 2560), (2, 4096, 128), (3, 64, 512), (1, 65536, 256)])
+def test_groupnorm_affine_matches_torch(B, HW, C):
+    from o2345 import ops_a
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = (torch.randn(B, HW, C, device="cuda", generator=g) * 2 + 0.5).half()
+    gamma, beta = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    for _ in range(2):                                         # second call: the scratch must have been left zeroed
+        scale, shift = ops_a.groupnorm_stats(x.view(-1, C), B, HW, C, 32, 1e-5, gamma, beta)
+        y, _, _ = ops_a.norm_act_im2col(x.view(-1, C), B, HW, 1, C, 1, 1, False, (scale, shift), True)
+        want = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+        assert (y.float().view(B, HW, C) - want).abs().max().item() < 2e-2
