@@ -8,9 +8,10 @@ rows = [r for r in csv.reader(open(sys.argv[1], errors="replace")) if len(r) > 6
 h = rows[0]
 ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
 tot, cnt = defaultdict(float), defaultdict(int)
-for r in rows[1:]:
-    if r[h.index("Metric Name")] != "gpu__time_duration.sum":
-        continue
+data = [r for r in rows[1:] if r[h.index("Metric Name")] == "gpu__time_duration.sum"]
+if len(sys.argv) > 3:                      # keep only the last N launches (e.g. the second, warm forward of two)
+    data = data[-int(sys.argv[3]):]
+for r in data:
     v = float(r[vi].replace(",", ""))
     v *= {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6, "ms": 1.0, "msecond": 1.0}.get(r[ui], 1e-6)
     name = re.sub(r"\(.*$", "", r[ki])
