@@ -283,6 +283,11 @@ int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, i
  * tiles alone cannot fill the GPU the K range is split over several CTAs per tile that accumulate into it, and a finalize
  * kernel applies the epilogue and leaves it zeroed again. */
 
+/* Diagnostic hook (not part of the data path): when device_buf16 != NULL, CTA (0,0,0) of every following CTA-pair GEMM
+ * launch stores clock64() stamps of its phases into device_buf16[0..8] (entry, prologue done, first TMA issued, last TMA
+ * issued, first operands landed, last MMA issued, accumulator ready, epilogue done, exit).  NULL switches it off. */
+void o2345_debug_gemm_trace(long long* device_buf16);
+
 /* Implicit-GEMM 3x3 convolution, stride 1, zero padding 1 (nn.Conv2d(C, N, 3, padding=1) of the UNet ResBlocks and the
  * VAE ResnetBlocks): x channel-last [B,H,W,C] fp16, weight [N, 9*C] fp16 in (ky,kx,c) order, out [B*H*W, N] (row stride
  * ldc).  No im2col buffer exists: the nine shifted windows are fetched by 4-D TMA boxes whose out-of-bounds zero fill is

@@ -164,7 +164,13 @@ struct GemmParams {
   // tile accumulate with fp32 reductions into ws [M, N] (zero on entry), a second kernel applies the epilogue and re-zeroes.
   int splits;
   float* ws;
+  int staged;                  // fp16 output through a shared-memory transpose so that global stores are coalesced rows
+  long long* trace;            // diagnostic: CTA (0,0,0) stores clock64() stamps of its phases (o2345_debug_gemm_trace), else nullptr
 };
+
+__device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = clock64();
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -263,6 +269,132 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
+constexpr int EPI_RB_GROUPS = 8;                 // row-bias groups (images) one 128-row tile may span when staged in smem
+constexpr int epi_smem_bytes(int bn) { return bn * 4 + EPI_RB_GROUPS * bn * 2; }
+
+// Called by the four epilogue warps while the main loop runs: the tile's bias and row-group-bias slices go to shared
+// memory, so that the epilogue proper never waits on a first-touch global load (r1 trace: five serialized L2 misses).
+template <int BN>
+__device__ __forceinline__ void epilogue_preload(const GemmParams& p, int m0, int n0, float* sbias, __half* srb, int tid_e) {
+  if (p.splits <= 1) {
+    for (int i = tid_e; i < BN; i += 128) sbias[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+    if (p.rowbias) {
+      const int g0 = m0 / p.rows_per_group;
+      const int last = (m0 + BM - 1 < p.M ? m0 + BM - 1 : p.M - 1) / p.rows_per_group;
+      const int ng = last - g0 + 1;
+      if (ng >= 1 && ng <= EPI_RB_GROUPS)
+        for (int i = tid_e; i < ng * BN; i += 128) {
+          const int gi = i / BN, c = i - gi * BN;
+          srb[i] = (n0 + c < p.N) ? p.rowbias[(int64_t)(g0 + gi) * p.rowbias_ld + n0 + c] : __float2half(0.f);
+        }
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+}
+
+// Staged epilogue of one warp's 32 accumulator rows x BN columns (fp16 output).  Phase 1: thread = row, as the TMEM
+// load delivers it: alpha / bias / row-group bias / activation / GEGLU gate, rounded to fp16 (where autocast rounds the
+// layer output) into this warp's slab of the (now idle) operand ring.  Phase 2: the warp walks the slab in 16-byte
+// pieces along rows, adds the residual and writes whole rows: every global access is a run of full 32-byte sectors, and
+// the residual loads of four pieces are in flight together.
+// (r1 trace: with one 16-byte store per lane to 32 different rows the epilogue took 46 000 cycles per tile, 10x the
+// main loop of a K = 320 GEMM.)
+template <int BN>
+__device__ __forceinline__ void epilogue_staged(const GemmParams& p, uint32_t tmem_row_base, uint8_t* slab, int lane, int m0,
+                                                int row0, int n0, const float* sbias, const __half* srb) {
+  const bool geglu = p.act == 3;
+  const int outc = geglu ? BN / 2 : BN;           // output columns of this tile
+  const int stride = outc * 2 + 16;               // bytes per staged row (+16: 16-byte pieces of consecutive rows rotate banks)
+  const int row = row0 + lane;
+  // row-group bias of this thread's row: from the smem copy when the tile spans few groups, else straight from global
+  const __half* rb = nullptr;
+  bool rb_smem = false;
+  if (p.rowbias) {
+    const int rr = row < p.M ? row : p.M - 1;
+    const int g0 = m0 / p.rows_per_group, last = (m0 + BM - 1 < p.M ? m0 + BM - 1 : p.M - 1) / p.rows_per_group;
+    rb_smem = last - g0 + 1 <= EPI_RB_GROUPS;
+    rb = rb_smem ? srb + (rr / p.rows_per_group - g0) * BN : p.rowbias + (int64_t)(rr / p.rows_per_group) * p.rowbias_ld + n0;
+  }
+  uint8_t* mine = slab + lane * stride;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_row_base + c0, r);
+    if (n0 + c0 >= p.N) break;                     // warp-uniform
+    if (geglu) {
+      __half2 h[8];
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        float a0 = fmaf(__uint_as_float(r[e]), p.alpha, sbias[c0 + e]), a1 = fmaf(__uint_as_float(r[e + 1]), p.alpha, sbias[c0 + e + 1]);
+        float g0 = fmaf(__uint_as_float(r[16 + e]), p.alpha, sbias[c0 + 16 + e]);
+        float g1 = fmaf(__uint_as_float(r[17 + e]), p.alpha, sbias[c0 + 17 + e]);
+        h[e >> 1] = __floats2half2_rn(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+      }
+      uint4* d = reinterpret_cast<uint4*>(mine + (c0 >> 1) * 2);
+      d[0] = reinterpret_cast<uint4*>(h)[0], d[1] = reinterpret_cast<uint4*>(h)[1];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + j), b1 = *reinterpret_cast<const float4*>(sbias + c0 + j + 4);
+        v[0] = b0.x, v[1] = b0.y, v[2] = b0.z, v[3] = b0.w, v[4] = b1.x, v[5] = b1.y, v[6] = b1.z, v[7] = b1.w;
+        if (rb) {
+          if (rb_smem || n0 + c0 + j + 8 <= p.N) {
+            uint4 q = *reinterpret_cast<const uint4*>(rb + c0 + j);
+            const __half* hq = reinterpret_cast<const __half*>(&q);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += __half2float(hq[e]);
+          }
+        }
+        __half2 h[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          float x0 = fmaf(__uint_as_float(r[j + e]), p.alpha, v[e]), x1 = fmaf(__uint_as_float(r[j + e + 1]), p.alpha, v[e + 1]);
+          h[e >> 1] = __floats2half2_rn(apply_act(x0, p.act), apply_act(x1, p.act));
+        }
+        *reinterpret_cast<uint4*>(mine + (c0 + j) * 2) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+  }
+  __syncwarp();
+  const int ppr = outc >> 3;                       // 16-byte pieces per row
+  const int total = 32 * ppr;
+  const int nout = geglu ? p.N >> 1 : p.N, n0out = geglu ? n0 >> 1 : n0;
+  __half* C = reinterpret_cast<__half*>(p.C);
+  constexpr int UN = 4;
+  for (int base = lane; base < total; base += 32 * UN) {
+    uint4 v[UN], q[UN];
+    int64_t o[UN];
+    bool ok[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int pp = base + 32 * u;
+      const int rl = pp / ppr, ci = pp - rl * ppr;
+      const int grow = row0 + rl, col = n0out + ci * 8;
+      ok[u] = pp < total && grow < p.M && col < nout;   // N is a multiple of 8 on this path (host check): no partial pieces
+      o[u] = (int64_t)grow * p.ldc + col;
+      if (ok[u]) {
+        v[u] = *reinterpret_cast<const uint4*>(slab + rl * stride + ci * 16);
+        if (p.residual) q[u] = *reinterpret_cast<const uint4*>(p.residual + o[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (!ok[u]) continue;
+      if (p.residual) {
+        __half2* a = reinterpret_cast<__half2*>(&v[u]);
+        const __half2* b = reinterpret_cast<const __half2*>(&q[u]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 fa = __half22float2(a[e]), fb = __half22float2(b[e]);
+          a[e] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(C + o[u]) = v[u];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ single-CTA kernel
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
@@ -277,6 +409,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);
+  __half* srb = reinterpret_cast<__half*>(sbias + BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, bz = blockIdx.z;
@@ -346,16 +480,22 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {  // ------------------------ epilogue warps 2..5, TMEM lane quarter = warp % 4
     const int quarter = warp & 3;
+    if (p.staged) epilogue_preload<BN>(p, m0, n0, sbias, srb, threadIdx.x - 64);
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = m0 + quarter * 32 + lane;
-    const int64_t crow = (p.batched ? (int64_t)(bz % p.nh) * p.stride_c_h + (int64_t)(bz / p.nh) * p.stride_c_b : 0) +
-                         (int64_t)row * p.ldc;
+    if (p.staged) {   // operand ring is idle once the accumulator is complete: reuse it for the output transpose
+      epilogue_staged<BN>(p, tmem_base + ((uint32_t)(quarter * 32) << 16), smem + quarter * 32 * (BN * 2 + 16), lane, m0,
+                          m0 + quarter * 32, n0, sbias, srb);
+    } else {
+      const int64_t crow = (p.batched ? (int64_t)(bz % p.nh) * p.stride_c_h + (int64_t)(bz / p.nh) * p.stride_c_b : 0) +
+                           (int64_t)row * p.ldc;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-      if (row < p.M) epilogue_chunk(p, r, row, crow, n0 + c0);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
+        if (row < p.M) epilogue_chunk(p, r, row, crow, n0 + c0);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -384,8 +524,11 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);
+  __half* srb = reinterpret_cast<__half*>(sbias + BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) stamp(p, 0);
   const uint32_t rank = cluster_ctarank();                    // 0 = leader (issues the MMAs, owns the full barriers)
   const int m0 = (blockIdx.x >> 1) * (2 * BM) + (int)rank * BM, n0 = blockIdx.y * BN, bz = blockIdx.z;
   const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
@@ -411,6 +554,7 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();   // barrier inits of the leader must be visible before the peer's TMA can complete on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(p, 1);
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer (both CTAs): own 128 rows of A, own half of the B tile
@@ -429,7 +573,9 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma2_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * BK, m0);
           tma2_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * BK, nb);
         }
+        if (kb == kb0) stamp(p, 2);
       }
+      stamp(p, 3);
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {  // ---------------- MMA issuer (leader only): M = 256 across the pair
@@ -438,6 +584,7 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int s = (kb - kb0) % STAGES;
         uint32_t ph = ((kb - kb0) / STAGES) & 1;
         mbar_wait(full + s, ph);
+        if (kb == kb0) stamp(p, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
 #pragma unroll
@@ -446,19 +593,28 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         umma2_commit(empty + s);   // frees this stage in both CTAs
       }
       umma2_commit(tmem_full);     // accumulator complete: both epilogues may start
+      stamp(p, 5);
     }
   } else {  // ------------------------ epilogue warps 2..5 on this CTA's 128 accumulator rows
     const int quarter = warp & 3;
+    if (p.staged) epilogue_preload<BN>(p, m0, n0, sbias, srb, threadIdx.x - 64);
     mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) stamp(p, 6);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = m0 + quarter * 32 + lane;
-    const int64_t crow = (int64_t)row * p.ldc;
+    if (p.staged) {   // operand ring is idle once the accumulator is complete: reuse it for the output transpose
+      epilogue_staged<BN>(p, tmem_base + ((uint32_t)(quarter * 32) << 16), smem + quarter * 32 * (BN * 2 + 16), lane, m0,
+                          m0 + quarter * 32, n0, sbias, srb);
+    } else {
+      const int64_t crow = (int64_t)row * p.ldc;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-      if (row < p.M) epilogue_chunk(p, r, row, crow, n0 + c0);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
+        if (row < p.M) epilogue_chunk(p, r, row, crow, n0 + c0);
+      }
     }
+    if (threadIdx.x == 64) stamp(p, 7);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or the peer's TMEM reads are in flight
@@ -466,6 +622,7 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
   }
+  if (threadIdx.x == 0) stamp(p, 8);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -561,6 +718,13 @@ int pick_splits(const GemmParams& p, int ctas, float* ws, int64_t ws_floats) {
   return s < 2 ? 1 : s;
 }
 
+// coalesced (shared-memory staged) epilogue: fp16 output, whole 16-byte pieces, one pass (no split-K, no head batches)
+void pick_staged(GemmParams& p) {
+  const int nout = p.act == 3 ? p.N / 2 : p.N;
+  p.staged = !p.out_f32 && p.splits <= 1 && !p.batched && (nout % 8) == 0 && (p.ldc % 8) == 0 && ((uintptr_t)p.C % 16) == 0 &&
+             (!p.residual || ((uintptr_t)p.residual % 16) == 0);
+}
+
 int finalize(const GemmParams& p, cudaStream_t st) {
   if (p.splits <= 1) return O2345_OK;
   const int vec = (p.N % 8) == 0 && (p.ldc % 8) == 0 && (!p.rowbias || (p.rowbias_ld % 8) == 0);
@@ -572,7 +736,7 @@ int finalize(const GemmParams& p, cudaStream_t st) {
 
 template <int BN, int STAGES>
 int launch1(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + epi_smem_bytes(BN) + 1024;
   static bool attr = false;
   if (!attr) {
     O2345_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -586,7 +750,7 @@ int launch1(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int
 
 template <int BN, int STAGES>
 int launch2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 1) * 8 + 16 + epi_smem_bytes(BN) + 1024;
   static bool attr = false;
   if (!attr) {
     O2345_CUDA(cudaFuncSetAttribute(gemm2_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -606,9 +770,11 @@ int pick_bn2(int N) {
   return N % 256 == 0 || N > 640 ? 256 : (N % 128 == 0 ? 128 : 160);
 }
 
+long long* g_trace = nullptr;
+
 int fill_epilogue(GemmParams& p, const o2345_epilogue* ep, int M, int N, int64_t ldc) {
   p.bias = nullptr, p.rowbias = nullptr, p.rowbias_ld = 0, p.rows_per_group = 1, p.residual = nullptr;
-  p.out_f32 = 0, p.act = 0, p.alpha = 1.f;
+  p.out_f32 = 0, p.act = 0, p.alpha = 1.f, p.trace = g_trace;
   if (!ep) return O2345_OK;
   O2345_CHECK_ARG(ep->act >= 0 && ep->act <= 3, "unknown activation");
   O2345_CHECK_ARG(!ep->rowbias || (ep->rows_per_group > 0 && (ep->rowbias_ld % 8) == 0 && ((uintptr_t)ep->rowbias % 16) == 0),
@@ -632,6 +798,8 @@ int dispatch2(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmPa
 }  // namespace o2345
 
 using namespace o2345;
+
+extern "C" void o2345_debug_gemm_trace(long long* device_buf16) { g_trace = device_buf16; }
 
 extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
                                  const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream) {
@@ -667,11 +835,13 @@ extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, cons
     rc = make_map(&mb, weight, N, 9 * (int64_t)C, 9 * (int64_t)C, 0, 0, 0, 0, 64);
     if (rc) return rc;
     p.splits = pick_splits(p, cdiv(p.M, BM), splitk_ws, ws_floats);
+    pick_staged(p);
     return launch1<64, 4>(ma, mb, p, 0, st);
   }
   rc = make_map(&mb, weight, N, 9 * (int64_t)C, 9 * (int64_t)C, 0, 0, 0, 0, bn / 2);
   if (rc) return rc;
   p.splits = pick_splits(p, 2 * cdiv(p.M, 2 * BM) * cdiv(N, bn), splitk_ws, ws_floats);
+  pick_staged(p);
   return dispatch2(bn, ma, mb, p, st);
 }
 
@@ -703,6 +873,7 @@ extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int 
     rc = make_map(&mb, B, N, K, ldb, nh, nb, stride_b_h, stride_b_b, BN1);
     if (rc) return rc;
     p.splits = pick_splits(p, cdiv(N, BN1) * cdiv(M, BM), splitk_ws, ws_floats);
+    pick_staged(p);
     const int batch = nh > 0 ? nh * nb : 0;
     if (BN1 == 64) return launch1<64, 4>(ma, mb, p, batch, st);
     return launch1<128, 3>(ma, mb, p, batch, st);
@@ -710,5 +881,6 @@ extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int 
   rc = make_map(&mb, B, N, K, ldb, 0, 0, 0, 0, bn / 2);
   if (rc) return rc;
   p.splits = pick_splits(p, 2 * cdiv(M, 2 * BM) * cdiv(N, bn), splitk_ws, ws_floats);
+  pick_staged(p);
   return dispatch2(bn, ma, mb, p, st);
 }

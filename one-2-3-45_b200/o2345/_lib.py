@@ -78,6 +78,7 @@ _SIGS = {
                                      C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "o2345_gemm_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int,
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
+    "o2345_debug_gemm_trace": (None, [c_fp]),
     "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64,
                                     C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
     "o2345_groupnorm_scratch_floats": (c_i64, [C.c_int, C.c_int]),
