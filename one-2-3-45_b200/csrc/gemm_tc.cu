@@ -292,6 +292,58 @@ __device__ __forceinline__ void epilogue_preload(const GemmParams& p, int m0, in
   asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+  if (ACT == 1) return __fdividef(x, 1.f + __expf(-x));
+  if (ACT == 2) return gelu_erf(x);
+  return x;
+}
+
+// Phase 1 of the staged epilogue for one thread (= one accumulator row): TMEM -> registers -> alpha / bias / row-group
+// bias / activation (ACT 3: GEGLU gate) -> fp16 -> this row of the warp's shared-memory slab.
+template <int BN, int ACT>
+__device__ __forceinline__ void stage_rows(const GemmParams& p, uint32_t tmem_row_base, uint8_t* mine, int n0, const float* sbias,
+                                           const __half* rb, bool rb_smem) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_row_base + c0, r);
+    if (n0 + c0 >= p.N) break;                     // warp-uniform
+    if (ACT == 3) {
+      __half2 h[8];
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        float a0 = fmaf(__uint_as_float(r[e]), p.alpha, sbias[c0 + e]), a1 = fmaf(__uint_as_float(r[e + 1]), p.alpha, sbias[c0 + e + 1]);
+        float g0 = fmaf(__uint_as_float(r[16 + e]), p.alpha, sbias[c0 + 16 + e]);
+        float g1 = fmaf(__uint_as_float(r[17 + e]), p.alpha, sbias[c0 + 17 + e]);
+        h[e >> 1] = __floats2half2_rn(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+      }
+      uint4* d = reinterpret_cast<uint4*>(mine + (c0 >> 1) * 2);
+      d[0] = reinterpret_cast<uint4*>(h)[0], d[1] = reinterpret_cast<uint4*>(h)[1];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + j), b1 = *reinterpret_cast<const float4*>(sbias + c0 + j + 4);
+        v[0] = b0.x, v[1] = b0.y, v[2] = b0.z, v[3] = b0.w, v[4] = b1.x, v[5] = b1.y, v[6] = b1.z, v[7] = b1.w;
+        if (rb && (rb_smem || n0 + c0 + j + 8 <= p.N)) {
+          uint4 q = *reinterpret_cast<const uint4*>(rb + c0 + j);
+          const __half* hq = reinterpret_cast<const __half*>(&q);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += __half2float(hq[e]);
+        }
+        __half2 h[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          float x0 = fmaf(__uint_as_float(r[j + e]), p.alpha, v[e]), x1 = fmaf(__uint_as_float(r[j + e + 1]), p.alpha, v[e + 1]);
+          h[e >> 1] = __floats2half2_rn(act_fn<ACT>(x0), act_fn<ACT>(x1));
+        }
+        *reinterpret_cast<uint4*>(mine + (c0 + j) * 2) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+  }
+}
+
 // Staged epilogue of one warp's 32 accumulator rows x BN columns (fp16 output).  Phase 1: thread = row, as the TMEM
 // load delivers it: alpha / bias / row-group bias / activation / GEGLU gate, rounded to fp16 (where autocast rounds the
 // layer output) into this warp's slab of the (now idle) operand ring.  Phase 2: the warp walks the slab in 16-byte
@@ -316,45 +368,12 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, uint32_t tm
     rb = rb_smem ? srb + (rr / p.rows_per_group - g0) * BN : p.rowbias + (int64_t)(rr / p.rows_per_group) * p.rowbias_ld + n0;
   }
   uint8_t* mine = slab + lane * stride;
-#pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(tmem_row_base + c0, r);
-    if (n0 + c0 >= p.N) break;                     // warp-uniform
-    if (geglu) {
-      __half2 h[8];
-#pragma unroll
-      for (int e = 0; e < 16; e += 2) {
-        float a0 = fmaf(__uint_as_float(r[e]), p.alpha, sbias[c0 + e]), a1 = fmaf(__uint_as_float(r[e + 1]), p.alpha, sbias[c0 + e + 1]);
-        float g0 = fmaf(__uint_as_float(r[16 + e]), p.alpha, sbias[c0 + 16 + e]);
-        float g1 = fmaf(__uint_as_float(r[17 + e]), p.alpha, sbias[c0 + 17 + e]);
-        h[e >> 1] = __floats2half2_rn(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
-      }
-      uint4* d = reinterpret_cast<uint4*>(mine + (c0 >> 1) * 2);
-      d[0] = reinterpret_cast<uint4*>(h)[0], d[1] = reinterpret_cast<uint4*>(h)[1];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float v[8];
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0 + j), b1 = *reinterpret_cast<const float4*>(sbias + c0 + j + 4);
-        v[0] = b0.x, v[1] = b0.y, v[2] = b0.z, v[3] = b0.w, v[4] = b1.x, v[5] = b1.y, v[6] = b1.z, v[7] = b1.w;
-        if (rb) {
-          if (rb_smem || n0 + c0 + j + 8 <= p.N) {
-            uint4 q = *reinterpret_cast<const uint4*>(rb + c0 + j);
-            const __half* hq = reinterpret_cast<const __half*>(&q);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += __half2float(hq[e]);
-          }
-        }
-        __half2 h[4];
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          float x0 = fmaf(__uint_as_float(r[j + e]), p.alpha, v[e]), x1 = fmaf(__uint_as_float(r[j + e + 1]), p.alpha, v[e + 1]);
-          h[e >> 1] = __floats2half2_rn(apply_act(x0, p.act), apply_act(x1, p.act));
-        }
-        *reinterpret_cast<uint4*>(mine + (c0 + j) * 2) = *reinterpret_cast<uint4*>(h);
-      }
-    }
+  // the activation switch is hoisted out of the element loops: one branch per tile instead of two per element
+  switch (p.act) {
+    case 1: stage_rows<BN, 1>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
+    case 2: stage_rows<BN, 2>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
+    case 3: stage_rows<BN, 3>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
+    default: stage_rows<BN, 0>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
   }
   __syncwarp();
   const int ppr = outc >> 3;                       // 16-byte pieces per row
