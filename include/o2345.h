@@ -237,9 +237,11 @@ typedef struct o2345_views {
  * direction = normalised (query_center - p) (Projector.compute); 1: dirs [n,3] given
  * (compute_view_independent, surface normals).  rnet_pack: O2345_RNET_PACK_FLOATS floats, every
  * matrix stored [in][out] in the order documented in csrc/render.cu. */
+#define O2345_BLEND_FP32 0     /* fp32 FMA mat-vecs in the reference's operation order (tight oracle parity)            */
+#define O2345_BLEND_TC_FP16 1  /* per-(sample, view) MLPs as mma.sync products: fp16 operands, fp32 accumulate / statistics */
 int o2345_render_blend(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl,
                        const float* occ, int D, const o2345_views* views, int dir_mode, const float* query_center,
-                       const float* dirs, const float* rnet_pack, float* rgb, int32_t* nvalid,
+                       const float* dirs, const float* rnet_pack, int precision, float* rgb, int32_t* nvalid,
                        o2345_stream_t stream);
 
 /* NeuS alpha from (sdf, grad), transmittance, colour/depth compositing.  Outputs: color [R,3], depth [R],

@@ -5,8 +5,8 @@
 //
 // Head dims are 40 / 80 / 160 and sequences 16..1024 tokens: far too small per (batch, head) to fill a 128-row tcgen05
 // tile pipeline, so this kernel uses warp-level mma.sync.m16n8k16 (fp16 in, fp32 accumulate) in the FlashAttention-2
-// arrangement: one CTA = 4 warps = 64 queries of one (b, h); K / V stream through shared memory in 64-key tiles (V stored
-// transposed so that both B operands are 32-bit shared loads); online softmax in fp32 registers with exp2; the S
+// arrangement: one CTA = 4 warps = 64 queries of one (b, h); K / V stream through shared memory in 64-key tiles (both row-major;
+// the P V operand comes out of ldmatrix.trans); online softmax in fp32 registers with exp2; the S
 // accumulator fragments are re-used in place as the A fragments of the P V product.  The arithmetic is softmax-bound
 // (N^2 exps per head), not tensor-bound, at these sizes.
 #include <cuda_fp16.h>
@@ -32,11 +32,11 @@ template <int D, int DP>  // head dim and its padding to a multiple of 16
 __global__ void __launch_bounds__(128)
 attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v, int N, int H, int ld,
                  __half* __restrict__ out, int ldo, float scale_log2) {
-  constexpr int LDQ = DP + 8, LDV = KT + 8, KS = DP / 16, NO = DP / 8;
+  constexpr int LDQ = DP + 8, KS = DP / 16, NO = DP / 8;
   extern __shared__ __align__(16) __half smem_h[];
   __half* sQ = smem_h;
   __half* sK = sQ + QT * LDQ;
-  __half* sVt = sK + KT * LDQ;
+  __half* sV = sK + KT * LDQ;              // row-major [key][d] like K; the PV operand is read with ldmatrix.trans
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
   const int q0 = blockIdx.x * QT;
@@ -64,20 +64,17 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
   for (int n = 0; n < NO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
 
+  // padding columns d..DP-1 of K and V are written once; the tile loads below only touch the first d columns
+  for (int i = tid; i < 2 * KT * LDQ / 8; i += 128) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);
   for (int k0 = 0; k0 < N; k0 += KT) {
-    __syncthreads();  // previous tile fully consumed
-    for (int i = tid; i < KT * LDQ / 8; i += 128) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < DP * LDV / 8; i += 128) reinterpret_cast<uint4*>(sVt)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
+    __syncthreads();  // previous tile fully consumed (first pass: zero fill visible)
     for (int i = tid; i < KT * CH; i += 128) {
       int r = i / CH, c = i % CH;
-      if (k0 + r < N) {
-        *reinterpret_cast<uint4*>(sK + r * LDQ + 8 * c) = *reinterpret_cast<const uint4*>(k + base + (int64_t)(k0 + r) * ld + 8 * c);
-        uint4 vv = *reinterpret_cast<const uint4*>(v + base + (int64_t)(k0 + r) * ld + 8 * c);
-        const __half* hv = reinterpret_cast<const __half*>(&vv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sVt[(8 * c + e) * LDV + r] = hv[e];
-      }
+      const bool in = k0 + r < N;
+      // rows past N: K garbage is masked after the product; V must be finite (0 * NaN), so it is zeroed
+      const int64_t off = base + (int64_t)(in ? k0 + r : 0) * ld + 8 * c;
+      *reinterpret_cast<uint4*>(sK + r * LDQ + 8 * c) = *reinterpret_cast<const uint4*>(k + off);
+      *reinterpret_cast<uint4*>(sV + r * LDQ + 8 * c) = in ? *reinterpret_cast<const uint4*>(v + off) : make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     // ---- S = Q K^T for this warp's 16 queries x 64 keys
@@ -125,8 +122,11 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
                         pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
 #pragma unroll
       for (int n = 0; n < NO; ++n) {
-        const __half* pv = sVt + (8 * n + g) * LDV + 16 * kk + 2 * t;
-        mma16816(o[n], pa, *reinterpret_cast<const uint32_t*>(pv), *reinterpret_cast<const uint32_t*>(pv + 8));
+        // B fragment of P V: keys 16 kk .. +15 (k) x head dims 8 n .. +7 (n) out of the row-major V tile
+        uint32_t b0, b1;
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sV + (16 * kk + (lane & 15)) * LDQ + 8 * n);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+        mma16816(o[n], pa, b0, b1);
       }
     }
   }
@@ -158,7 +158,7 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
   float sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream;
   const __half *qh = (const __half*)q, *kh = (const __half*)k, *vh = (const __half*)v;
-  auto smem = [](int dp) { return (size_t)((QT + KT) * (dp + 8) + dp * (KT + 8)) * sizeof(__half); };
+  auto smem = [](int dp) { return (size_t)((QT + 2 * KT) * (dp + 8)) * sizeof(__half); };
   static bool attr = false;
   if (!attr) {
     O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(160)));

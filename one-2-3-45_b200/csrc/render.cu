@@ -616,15 +616,25 @@ extern "C" int o2345_ray_midpoints(const float* rays_o, const float* rays_d, int
   return O2345_OK;
 }
 
+namespace o2345 {
+int launch_render_blend_tc(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl, const float* occ, int D,
+                           const o2345_views* views, int dir_mode, const float* query_center, const float* dirs,
+                           const float* rnet_pack, float* rgb, int32_t* nvalid, cudaStream_t st);   // render_tc.cu
+}
+
 extern "C" int o2345_render_blend(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl,
                                   const float* occ, int D, const o2345_views* views, int dir_mode,
-                                  const float* query_center, const float* dirs, const float* rnet_pack, float* rgb,
-                                  int32_t* nvalid, o2345_stream_t stream) {
+                                  const float* query_center, const float* dirs, const float* rnet_pack, int precision,
+                                  float* rgb, int32_t* nvalid, o2345_stream_t stream) {
   O2345_CHECK_ARG(src && vol_cl && occ && views && rnet_pack && rgb, "null pointer");
   O2345_CHECK_ARG(src->mode == O2345_PTS_EXPLICIT || src->mode == O2345_PTS_RAYS, "explicit or ray points only");
   O2345_CHECK_ARG(views->V >= 1 && views->V <= 32 && views->maps && views->proj && views->centers, "1..32 views");
   O2345_CHECK_ARG((dir_mode == 0 && query_center) || (dir_mode == 1 && dirs), "direction source missing");
+  O2345_CHECK_ARG(precision == O2345_BLEND_FP32 || precision == O2345_BLEND_TC_FP16, "unknown precision");
   if (n == 0) return O2345_OK;
+  if (precision == O2345_BLEND_TC_FP16)
+    return launch_render_blend_tc(src, n, active, vol_cl, occ, D, views, dir_mode, query_center, dirs, rnet_pack, rgb, nvalid,
+                                  (cudaStream_t)stream);
   static bool attr_done = false;
   if (!attr_done) {
     O2345_CUDA(cudaFuncSetAttribute(render_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLEND_SMEM));

@@ -35,6 +35,7 @@ class Epilogue(C.Structure):
 
 
 PTS_EXPLICIT, PTS_LATTICE, PTS_RAYS = 0, 1, 2
+BLEND_FP32, BLEND_TC_FP16 = 0, 1
 SDF_PACK_FLOATS = 39 * 128 + 128 + 2 * (144 * 128 + 128) + 128 * 144 + 128 * 48
 RNET_PACK_FLOATS = 19664
 MAP_CH = 60
@@ -75,7 +76,7 @@ _SIGS = {
     "o2345_ray_midpoints": (C.c_int, [c_fp, c_fp, c_i64, c_fp, C.c_int, C.c_float, c_fp, C.c_int, c_fp, c_fp,
                                       c_fp, c_fp]),
     "o2345_render_blend": (C.c_int, [C.POINTER(Points), c_i64, c_fp, c_fp, c_fp, C.c_int, C.POINTER(Views),
-                                     C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+                                     C.c_int, c_fp, c_fp, c_fp, C.c_int, c_fp, c_fp, c_fp]),
     "o2345_gemm_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int,
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
     "o2345_debug_gemm_trace": (None, [c_fp]),

@@ -296,13 +296,15 @@ class SourceViews:
                               centers=self.centers.data_ptr(), sizeW=float(sizeW), sizeH=float(sizeH))
 
 
-def render_blend(src: PointSource, active, vol_cl, occ, views: SourceViews, rnet_pack, query_center=None, dirs=None):
+def render_blend(src: PointSource, active, vol_cl, occ, views: SourceViews, rnet_pack, query_center=None, dirs=None,
+                 precision=L.BLEND_TC_FP16):
+    """precision: L.BLEND_TC_FP16 (tensor-core MLPs, fp16 operands / fp32 accumulate) or L.BLEND_FP32 (fp32 FMA)."""
     n, dev = src.n, vol_cl.device
     rgb = torch.empty(n, 3, dtype=_f32, device=dev)
     nvalid = torch.empty(n, dtype=_i32, device=dev)
     mode = 0 if dirs is None else 1
     L.call("o2345_render_blend", C.byref(src.struct), n, _p(active, _u8), _f(vol_cl), _f(occ), vol_cl.shape[0],
-           C.byref(views.struct), mode, _f(query_center), _f(dirs), _f(rnet_pack), _f(rgb), _p(nvalid, _i32),
+           C.byref(views.struct), mode, _f(query_center), _f(dirs), _f(rnet_pack), int(precision), _f(rgb), _p(nvalid, _i32),
            _stream())
     return rgb, nvalid
 

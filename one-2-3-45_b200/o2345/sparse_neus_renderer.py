@@ -18,6 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import _lib as L
 from . import ops
 from .featurenet import source_maps_channel_last
 from .sparse_sdf_network import channel_last_volume
@@ -36,6 +37,9 @@ class SparseNeuSRenderer(nn.Module):
         self.n_samples, self.n_importance, self.n_outside = n_samples, n_importance, n_outside
         self.perturb, self.alpha_type = perturb, alpha_type
         self.if_fitted_rendering = False
+        # view-blending MLPs: tensor-core kernel (fp16 operands, fp32 accumulate) by default; _lib.BLEND_FP32 selects the
+        # fp32 FMA kernel whose operation order follows the reference (used by the tight parity tests)
+        self.blend_precision = L.BLEND_TC_FP16
         self._views_key, self._views = None, None
         self._u = {}
 
@@ -106,7 +110,8 @@ class SparseNeuSRenderer(nn.Module):
         q = ops.sdf_query(src, vol_cl, pack, active=active, inactive_sdf=100.0, want_grad=True)
         views = self._source_views(feature_maps, color_maps, w2cs, intrinsics, img_wh)
         qc = ops.cf32(query_c2w.reshape(-1, 4, 4)[0, :3, 3])
-        color_pts, nvalid = ops.render_blend(src, active, vol_cl, occ, views, rendering_network.packed(), query_center=qc)
+        color_pts, nvalid = ops.render_blend(src, active, vol_cl, occ, views, rendering_network.packed(), query_center=qc,
+                                             precision=self.blend_precision)
         inv_s = self.variance_network.inv_s()
         bg = None if background_rgb is None else float(background_rgb)
         comp = ops.ray_composite(rays_d, mid, dists, q["sdf"], q["grad"], color_pts, active, nvalid, inv_s,
@@ -193,5 +198,6 @@ class SparseNeuSRenderer(nn.Module):
         g = ops.sdf_query(src, vol_cl, sdf_network.sdf_layer.packed(), want_grad=True)["grad"]
         normals = torch.nn.functional.normalize(g, p=2, dim=-1, eps=1e-6)
         views = self._source_views(feature_maps, color_maps, w2cs, intrinsics, img_wh)
-        rgb, _ = ops.render_blend(src, None, vol_cl, occ, views, rendering_network.packed(), dirs=normals.contiguous())
+        rgb, _ = ops.render_blend(src, None, vol_cl, occ, views, rendering_network.packed(), dirs=normals.contiguous(),
+                                  precision=self.blend_precision)
         return rgb, normals

@@ -159,7 +159,21 @@ def _render(tr, om, dev, vol, occ, fm):
         w2cs=om.w2cs.to(dev), intrinsics=om.intr.to(dev), img_wh=[MINI["W"], MINI["H"]], query_c2w=om.qc2w.to(dev))
 
 
-def test_render_against_oracle_same_volume(om, tr, dev):
+# blend kernels: 0 = fp32 FMA in the reference's operation order, 1 = tensor-core MLPs (fp16 operands, fp32 accumulate).
+# Colour tolerance of the tensor-core kernel: operands carry 2^-11 relative rounding through 11 small layers; the blend
+# weights are a softmax of O(1) logits and the colours are in [0, 1], so 3e-3 absolute bounds the drift (measured ~1e-3).
+BLEND_TOL = {0: 2e-4, 1: 3e-3}
+
+
+@pytest.fixture(params=[0, 1], ids=["blend_fp32", "blend_tc_fp16"])
+def precision(request, tr):
+    old = tr.sdf_renderer_lod0.blend_precision
+    tr.sdf_renderer_lod0.blend_precision = request.param
+    yield request.param
+    tr.sdf_renderer_lod0.blend_precision = old
+
+
+def test_render_against_oracle_same_volume(om, tr, dev, precision):
     """Ray marcher alone: both sides consume the ORACLE's volume and feature maps."""
     res = _render(tr, om, dev, om.volume.to(dev), om.occ.to(dev), om.fmaps.to(dev))
     st = om.st
@@ -174,7 +188,7 @@ def test_render_against_oracle_same_volume(om, tr, dev):
     same = dz < 1e-5                                    # rays whose 128 depths all agree to rounding
     print("rays with identical depth samples:", int(same.sum()), "of", len(same), "max dz", float(dz.max()))
     assert float(same.float().mean()) >= 0.5 and float(dz.max()) < 0.04
-    for k, kr, tol in (("color_fine", "color", 2e-4), ("depth", "depth", 2e-4), ("weights", "weights", 2e-4)):
+    for k, kr, tol in (("color_fine", "color", BLEND_TOL[precision]), ("depth", "depth", 2e-4), ("weights", "weights", 2e-4)):
         assert maxerr(res[k][same.to(dev)], ref[kr][same]) < tol, k
         assert maxerr(res[k], ref[kr]) < 5e-3, k          # rays that drew a different depth: still the same pixel
     assert torch.equal(res["color_fine_mask"].cpu(), ref["color_mask"])
@@ -182,9 +196,9 @@ def test_render_against_oracle_same_volume(om, tr, dev):
     assert float((res["gradients"].cpu()[same] - ref["gradients"][same]).abs().mean()) < 1e-4
 
 
-def test_render_end_to_end_against_reference_golden(om, tr, gpu, dev, golden):
+def test_render_end_to_end_against_reference_golden(om, tr, gpu, dev, golden, precision):
     res = _render(tr, om, dev, gpu["cond"]["dense_volume_scale0"], gpu["cond"]["valid_mask_volume_scale0"], gpu["fm"])
-    assert maxerr(res["color_fine"], golden["color"]) < 2e-3
+    assert maxerr(res["color_fine"], golden["color"]) < 2e-3 + BLEND_TOL[precision]
     assert maxerr(res["depth"], golden["depth"]) < 5e-3
     assert maxerr(res["weights"], golden["weights"]) < 5e-3
     for k in ("depth", "color_fine", "color_fine_mask", "variance", "cdf_fine", "depth_variance", "weights_sum",
@@ -193,15 +207,15 @@ def test_render_end_to_end_against_reference_golden(om, tr, gpu, dev, golden):
         assert res[k] is not None
 
 
-def test_vertex_colors(om, tr, dev, golden):
+def test_vertex_colors(om, tr, dev, golden, precision):
     rgb, nrm = tr.sdf_renderer_lod0.blend_points(
         om.verts.to(dev), tr.sdf_network_lod0, tr.rendering_network_lod0, om.volume.to(dev), om.occ.to(dev),
         om.fmaps.to(dev), om.imgs.to(dev), om.w2cs.to(dev), om.intr.to(dev), [MINI["W"], MINI["H"]])
     col, n_ref = O.vertex_colors(om.verts, om.volume, om.occ, om.fmaps, om.imgs, om.w2cs, om.intr,
                                  om.st["sdf_network_lod0"], om.st["rendering_network_lod0"], W=MINI["W"], H=MINI["H"])
     assert maxerr(nrm, n_ref) < 2e-4
-    assert maxerr(rgb, col) < 1e-3
-    assert maxerr(rgb, golden["vert_color"]) < 2e-3
+    assert maxerr(rgb, col) < 1e-3 + BLEND_TOL[precision]
+    assert maxerr(rgb, golden["vert_color"]) < 2e-3 + BLEND_TOL[precision]
 
 
 def test_marching_cubes_bit_exact_cases_and_vertex_set(om, tr, dev, golden):
@@ -326,3 +340,29 @@ def test_full_size_render_properties(full, dev):
                                     feature_maps=fmaps, color_maps=imgs, w2cs=sample["w2cs"][0],
                                     intrinsics=sample["intrinsics"][0], img_wh=[256, 256], query_c2w=sample["query_c2w"])
     assert torch.equal(a["color_fine"], c[:h])
+
+
+def test_full_size_blend_kernels_agree(full, dev):
+    """Tensor-core blend kernel against the fp32 one on a 32-view, 256x256 scene (same samples, same maps)."""
+    tr, sample, imgs, fmaps, cond = full
+    ro = sample["rays"]["rays_o"][0][::29][:2048].contiguous()
+    rd = sample["rays"]["rays_v"][0][::29][:2048].contiguous()
+    near, far = sample["query_near_far"][0, :1], sample["query_near_far"][0, 1:]
+    outs = {}
+    old = tr.sdf_renderer_lod0.blend_precision
+    try:
+        for prec in (0, 1):
+            tr.sdf_renderer_lod0.blend_precision = prec
+            outs[prec] = tr.sdf_renderer_lod0.render(
+                ro, rd, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0, perturb_overwrite=0, background_rgb=1.0,
+                alpha_inter_ratio=1.0, lod=0, conditional_volume=cond["dense_volume_scale0"],
+                conditional_valid_mask_volume=cond["valid_mask_volume_scale0"], feature_maps=fmaps, color_maps=imgs,
+                w2cs=sample["w2cs"][0], intrinsics=sample["intrinsics"][0], img_wh=[256, 256], query_c2w=sample["query_c2w"])
+    finally:
+        tr.sdf_renderer_lod0.blend_precision = old
+    a, b = outs[0]["color_fine"], outs[1]["color_fine"]
+    assert torch.equal(outs[0]["z_vals"], outs[1]["z_vals"])                 # the sampler does not depend on the colours
+    assert torch.equal(outs[0]["color_fine_mask"], outs[1]["color_fine_mask"])
+    d = (a - b).abs()
+    print("blend fp32 vs tensor-core: max", float(d.max()), "mean", float(d.mean()))
+    assert float(d.max()) < 3e-3 and float(d.mean()) < 3e-4
