@@ -161,8 +161,8 @@ def _render(tr, om, dev, vol, occ, fm):
 
 # blend kernels: 0 = fp32 FMA in the reference's operation order, 1 = tensor-core MLPs (fp16 operands, fp32 accumulate).
 # Colour tolerance of the tensor-core kernel: operands carry 2^-11 relative rounding through 11 small layers; the blend
-# weights are a softmax of O(1) logits and the colours are in [0, 1], so 3e-3 absolute bounds the drift (measured ~1e-3).
-BLEND_TOL = {0: 2e-4, 1: 3e-3}
+# weights are a softmax of O(1) logits and the colours are in [0, 1], and the measured drift against the fp32 kernel is 5e-5 max on the 32-view scene; 5e-4 is the stated bound.
+BLEND_TOL = {0: 2e-4, 1: 5e-4}
 
 
 @pytest.fixture(params=[0, 1], ids=["blend_fp32", "blend_tc_fp16"])
@@ -365,4 +365,4 @@ def test_full_size_blend_kernels_agree(full, dev):
     assert torch.equal(outs[0]["color_fine_mask"], outs[1]["color_fine_mask"])
     d = (a - b).abs()
     print("blend fp32 vs tensor-core: max", float(d.max()), "mean", float(d.mean()))
-    assert float(d.max()) < 3e-3 and float(d.mean()) < 3e-4
+    assert float(d.max()) < 5e-4 and float(d.mean()) < 5e-5
