@@ -29,7 +29,7 @@ namespace o2345 {
 namespace {
 using namespace rpack;
 
-constexpr int TW = 8;  // warps per CTA
+constexpr int TW = 10;  // warps per CTA (2 CTAs per SM: 20 warps; r1: 16 warps were latency / instruction-fetch bound)
 
 // fp16 weights in shared memory: matrix [n][LD], LD = K + 8 halves (conflict-free 32-bit loads by (g, t))
 constexpr int LD16 = 24, LD32 = 40, LD48 = 56, LD64 = 72, LD144 = 152;
@@ -53,8 +53,26 @@ constexpr int WARP_SMEM = 32 * REC * 4 + 2 * 16 * 32 * 4;
 constexpr int TC_SMEM = H_TOTAL * 2 + F_TOTAL * 4 + TW * WARP_SMEM;
 static_assert((H_TOTAL * 2) % 16 == 0, "bias block must stay 16-byte aligned");
 
-__device__ __forceinline__ float elu_(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
-__device__ __forceinline__ float sigm_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// Branch-free ELU: one MUFU.EX2 on min(x, 0) and a select (the ternary around __expf compiled to a divergent branch per
+// element: r1 ncu of this kernel showed BSSY/BSYNC/FSETP/PLOP3 at 20 % of the issued instructions).
+__device__ __forceinline__ float ex2_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu_(float x) {
+  const float e = ex2_(fminf(x, 0.f) * 1.4426950408889634f) - 1.f;
+  return x > 0.f ? x : e;
+}
+__device__ __forceinline__ float sigm_(float x) { return __fdividef(1.f, 1.f + ex2_(-1.4426950408889634f * x)); }
+// ELU on a packed pair that only feeds the next layer's fp16 operand: max(x, 0) + (2^(min(x, 0) log2 e) - 1) in half2
+__device__ __forceinline__ uint32_t elu_h2(uint32_t v) {
+  const __half2 x = *reinterpret_cast<const __half2*>(&v);
+  const __half2 zero = __float2half2_rn(0.f);
+  const __half2 e = h2exp2(__hmul2(__hmin2(x, zero), __float2half2_rn(1.4426950408889634f)));
+  const __half2 r = __hadd2(__hmax2(x, zero), __hsub2(e, __float2half2_rn(1.f)));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ uint32_t pack2(float x, float y) {
   __half2 h = __floats2half2_rn(x, y);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -88,6 +106,15 @@ __device__ __forceinline__ void to_frags(uint32_t (&a)[KB][4], const float (&c)[
     a[kb][0] = pack2(c[2 * kb][0], c[2 * kb][1]), a[kb][1] = pack2(c[2 * kb][2], c[2 * kb][3]);
     a[kb][2] = pack2(c[2 * kb + 1][0], c[2 * kb + 1][1]), a[kb][3] = pack2(c[2 * kb + 1][2], c[2 * kb + 1][3]);
   }
+}
+// ... with the ELU applied to the packed halves (layers whose output is only the next MMA operand)
+template <int KB>
+__device__ __forceinline__ void to_frags_elu(uint32_t (&a)[KB][4], const float (&c)[2 * KB][4]) {
+  to_frags<KB>(a, c);
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[kb][i] = elu_h2(a[kb][i]);
 }
 template <int NT>
 __device__ __forceinline__ void elu_all(float (&c)[NT][4]) {
@@ -129,12 +156,20 @@ __device__ __forceinline__ void sample_point(const o2345_points& src, int64_t gi
   }
 }
 
-// dst[n][col0 + k] = src[(k_src0 + k) * src_ld + n] for n < n_used, k < k_used; zero elsewhere in [n_rows][k_span]
+// Feature-channel order inside the MMA fragments.  A thread's four accumulator columns of one 16-column block are
+// {2t, 2t+1, 8+2t, 9+2t}; mapping fragment column p to map channel chan(p) = 16 (p / 16) + 4 t + 2 h + e makes them the
+// four CONSECUTIVE channels 16 kb + 4 t .. + 3, i.e. one 16-byte load per tap.  Every matrix whose k (or n) index is a
+// feature channel is stored with that permutation, so the arithmetic is unchanged.
+__host__ __device__ constexpr int chan(int p) { return 16 * (p / 16) + 4 * ((p % 8) / 2) + 2 * ((p % 16) / 8) + (p % 2); }
+
+// dst[n][col0 + k] = src[kmap(k) * src_ld + nmap(n)] for nmap(n) < n_used, kmap(k) < k_used; zero elsewhere in
+// [n_rows][k_span].  perm_k / perm_n: the index is a feature channel, stored in fragment order (chan()).
 __device__ void fill_w(__half* dst, int LD, int n_rows, int col0, int k_span, const float* __restrict__ src, int src_ld, int n_used,
-                       int k_used, int tid, int nthreads) {
+                       int k_used, int tid, int nthreads, bool perm_k = false, bool perm_n = false) {
   for (int i = tid; i < n_rows * k_span; i += nthreads) {
     int nrow = i / k_span, k = i - nrow * k_span;
-    float v = (nrow < n_used && k < k_used) ? __ldg(src + (int64_t)k * src_ld + nrow) : 0.f;
+    const int ns = perm_n ? chan(nrow) : nrow, ks = perm_k ? chan(k) : k;
+    float v = (ns < n_used && ks < k_used) ? __ldg(src + (int64_t)ks * src_ld + ns) : 0.f;
     dst[nrow * LD + col0 + k] = __float2half_rn(v);
   }
 }
@@ -150,11 +185,11 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
   const int tid = threadIdx.x, nth = blockDim.x;
   // ---- weights: fp32 [in][out] pack -> fp16 [out][in] rows
   fill_w(sW + H_D0, LD16, 16, 0, 16, pack + P_D0W, 16, 16, 4, tid, nth);
-  fill_w(sW + H_D1, LD16, 64, 0, 16, pack + P_D1W, 64, 64, 16, tid, nth);
+  fill_w(sW + H_D1, LD16, 64, 0, 16, pack + P_D1W, 64, 64, 16, tid, nth, false, true);
   fill_w(sW + H_BS, LD144, 64, 0, 16, pack + P_B0W, 64, 64, 16, tid, nth);
-  fill_w(sW + H_BS, LD144, 64, 16, 64, pack + P_B0W + 16 * 64, 64, 64, NF, tid, nth);
-  fill_w(sW + H_BS, LD144, 64, 80, 64, pack + P_B0W + 75 * 64, 64, 64, NF, tid, nth);
-  fill_w(sW + H_BV, LD64, 64, 0, 64, pack + P_B0W + 134 * 64, 64, 64, NF, tid, nth);
+  fill_w(sW + H_BS, LD144, 64, 16, 64, pack + P_B0W + 16 * 64, 64, 64, NF, tid, nth, true);
+  fill_w(sW + H_BS, LD144, 64, 80, 64, pack + P_B0W + 75 * 64, 64, 64, NF, tid, nth, true);
+  fill_w(sW + H_BV, LD64, 64, 0, 64, pack + P_B0W + 134 * 64, 64, 64, NF, tid, nth, true);
   fill_w(sW + H_B1, LD64, 32, 0, 64, pack + P_B1W, 32, 32, 64, tid, nth);
   fill_w(sW + H_V0, LD32, 32, 0, 32, pack + P_V0W, 32, 32, 32, tid, nth);
   fill_w(sW + H_V1, LD32, 40, 0, 32, pack + P_V1W, 32, 32, 32, tid, nth);
@@ -167,7 +202,7 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
   for (int i = tid; i < F_TOTAL; i += nth) {
     float v = 0.f;
     if (i < F_D1B) v = pack[P_D0B + i];
-    else if (i < F_B0B) v = pack[P_D1B + i - F_D1B];
+    else if (i < F_B0B) v = pack[P_D1B + chan(i - F_D1B)];   // output = feature channel: fragment order
     else if (i < F_B1B) v = pack[P_B0B + i - F_B0B];
     else if (i < F_V0B) v = pack[P_B1B + i - F_B1B];
     else if (i < F_V1B) v = pack[P_V0B + i - F_V0B];
@@ -310,7 +345,7 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
     float S[8][2], Q[8][2];
 #pragma unroll
     for (int j = 0; j < 8; ++j) S[j][0] = S[j][1] = Q[j][0] = Q[j][1] = 0.f;
-    float rgA[4], rgB[4];   // original colours of this thread's rows in tile 0 / 1 (t = 0: r, g; t = 1: b)
+    float rgA[6], rgB[6];   // original r, g, b of rows g and g + 8 in tile 0 / 1 (meaningful in the t == 0 lanes)
 
     // ================= pass A: features of every valid view, weighted first and second moments
     for (int tile = 0; tile < ntile; ++tile) {
@@ -332,24 +367,22 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
         const float* tp[4] = {m + ((int64_t)cy0 * W + cx0) * CM, m + ((int64_t)cy0 * W + cx1) * CM,
                               m + ((int64_t)cy1 * W + cx0) * CM, m + ((int64_t)cy1 * W + cx1) * CM};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = 8 * j + 2 * t;   // channels c, c + 1 of this row
-          float a0 = 0.f, a1 = 0.f;
+        for (int kb = 0; kb < 4; ++kb) {
+          const int c = 16 * kb + 4 * t;   // channels c .. c + 3 of this row = fragment columns {2t, 2t+1} of tiles 2kb, 2kb+1
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
           if (c < CM) {
 #pragma unroll
             for (int tap = 0; tap < 4; ++tap) {
-              const float2 v = __ldg(reinterpret_cast<const float2*>(tp[tap] + c));
-              a0 = fmaf(v.x, wq[tap], a0), a1 = fmaf(v.y, wq[tap], a1);
+              const float4 v = __ldg(reinterpret_cast<const float4*>(tp[tap] + c));
+              a0 = fmaf(v.x, wq[tap], a0), a1 = fmaf(v.y, wq[tap], a1), a2 = fmaf(v.z, wq[tap], a2), a3 = fmaf(v.w, wq[tap], a3);
             }
           }
-          F[j][2 * rr] = a0, F[j][2 * rr + 1] = a1;
+          F[2 * kb][2 * rr] = a0, F[2 * kb][2 * rr + 1] = a1, F[2 * kb + 1][2 * rr] = a2, F[2 * kb + 1][2 * rr + 1] = a3;
         }
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (tile == 0) rgA[i] = F[0][i];
-        else rgB[i] = F[0][i];
-      }
+      // original colours: channels 0, 1 = columns 0, 1 of tile 0, channel 2 = column 0 of tile 1 (chan()), all in t == 0
+      if (tile == 0) rgA[0] = F[0][0], rgA[1] = F[0][1], rgA[2] = F[1][0], rgA[3] = F[0][2], rgA[4] = F[0][3], rgA[5] = F[1][2];
+      else rgB[0] = F[0][0], rgB[1] = F[0][1], rgB[2] = F[1][0], rgB[3] = F[0][2], rgB[4] = F[0][3], rgB[5] = F[1][2];
       // direction feature: ray_dir_fc(ray_diff) = ELU(D1 . ELU(D0 . rd + b0) + b1), added to the fetched feature
       {
         uint32_t ard[1][4];
@@ -359,9 +392,8 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
         float c16[2][4];
         init_bias<2>(c16, sB + F_D0B, t);
         mm<1, 2>(c16, ard, sW + H_D0, LD16, g, t);
-        elu_all<2>(c16);
         uint32_t a16[1][4];
-        to_frags<1>(a16, c16);
+        to_frags_elu<1>(a16, c16);
         float c64[8][4];
         init_bias<8>(c64, sB + F_D1B, t);
         mm<1, 8>(c64, a16, sW + H_D1, LD16, g, t);
@@ -424,9 +456,8 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) c1[j][i] = hs[j][i];
       mm<4, 8>(c1, aF, sW + H_BV, LD64, g, t);
-      elu_all<8>(c1);
       uint32_t a1[4][4];
-      to_frags<4>(a1, c1);
+      to_frags_elu<4>(a1, c1);
       float x2[4][4];
       init_bias<4>(x2, sB + F_B1B, t);
       mm<4, 4>(x2, a1, sW + H_B1, LD64, g, t);
@@ -440,8 +471,7 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
       float hv[4][4];
       init_bias<4>(hv, sB + F_V0B, t);
       mm<2, 4>(hv, a2, sW + H_V0, LD32, g, t);
-      elu_all<4>(hv);
-      to_frags<2>(a2, hv);
+      to_frags_elu<2>(a2, hv);
       float rv[5][4];
       init_bias<5>(rv, sB + F_V1B, t);
       mm<2, 5>(rv, a2, sW + H_V1, LD32, g, t);
@@ -460,8 +490,7 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
       float h2[4][4];
       init_bias<4>(h2, sB + F_U0B, t);
       mm<2, 4>(h2, a2, sW + H_U0, LD32, g, t);
-      elu_all<4>(h2);
-      to_frags<2>(a2, h2);
+      to_frags_elu<2>(a2, h2);
       float u[1][4];
       init_bias<1>(u, sB + F_U1B, t);
       mm<2, 1>(u, a2, sW + H_U1, LD32, g, t);
@@ -482,9 +511,8 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
       float q1[2][4];
       init_bias<2>(q1, sB + F_R0B, t);
       mm<3, 2>(q1, a3, sW + H_R0, LD48, g, t);
-      elu_all<2>(q1);
       uint32_t a4[1][4];
-      to_frags<1>(a4, q1);
+      to_frags_elu<1>(a4, q1);
       float q2[1][4];
       init_bias<1>(q2, sB + F_R1B, t);
       mm<1, 1>(q2, a4, sW + H_R1, LD16, g, t);
@@ -501,11 +529,10 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
     const float eA0 = lgA0 > -1e38f ? __expf(lgA0 - lmax) : 0.f, eA1 = lgA1 > -1e38f ? __expf(lgA1 - lmax) : 0.f;
     const float eB0 = lgB0 > -1e38f ? __expf(lgB0 - lmax) : 0.f, eB1 = lgB1 > -1e38f ? __expf(lgB1 - lmax) : 0.f;
     float den = eA0 + eA1 + eB0 + eB1;
-    float acc0 = eA0 * rgA[0] + eA1 * rgA[2], acc1 = eA0 * rgA[1] + eA1 * rgA[3];
-    if (ntile > 1) acc0 += eB0 * rgB[0] + eB1 * rgB[2], acc1 += eB0 * rgB[1] + eB1 * rgB[3];
-    den = rows_sum(den), acc0 = rows_sum(acc0), acc1 = rows_sum(acc1);
-    if (lane == 0) rgb_out[3 * gi] = acc0 / den, rgb_out[3 * gi + 1] = acc1 / den;
-    if (lane == 1) rgb_out[3 * gi + 2] = acc0 / den;
+    float accr = eA0 * rgA[0] + eA1 * rgA[3], accg = eA0 * rgA[1] + eA1 * rgA[4], accb = eA0 * rgA[2] + eA1 * rgA[5];
+    if (ntile > 1) accr += eB0 * rgB[0] + eB1 * rgB[3], accg += eB0 * rgB[1] + eB1 * rgB[4], accb += eB0 * rgB[2] + eB1 * rgB[5];
+    den = rows_sum(den), accr = rows_sum(accr), accg = rows_sum(accg), accb = rows_sum(accb);
+    if (lane == 0) rgb_out[3 * gi] = accr / den, rgb_out[3 * gi + 1] = accg / den, rgb_out[3 * gi + 2] = accb / den;
     __syncwarp();
   }
 }

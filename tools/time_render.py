@@ -12,7 +12,18 @@ tr = build_networks(dev, vol_dim=bench.VOL, states=S.all_states(0), perturb=0.0)
 sample = synthetic_sample(dev, n_views=bench.N_VIEWS, H=bench.H, W=bench.W)
 imgs, fmaps, cond, sizeW, sizeH = tr._conditional_features(sample)
 pk = bench.peaks()
-for prec in (1, 0):
+from o2345 import ops
+_rb = ops.render_blend
+hist = {}
+def spy(*a, **k):
+    r = _rb(*a, **k)
+    if "h" not in hist:
+        nv = r[1][r[1] > 0]
+        hist["h"] = torch.bincount(nv, minlength=33).tolist()
+    return r
+ops.render_blend = spy
+for prec in (1,):
     tr.sdf_renderer_lod0.blend_precision = prec
     r = bench.render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk)
     print("precision", prec, json.dumps(r))
+print("nvalid histogram (first blend call, active samples):", hist.get("h"))
