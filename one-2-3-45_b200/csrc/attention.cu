@@ -32,6 +32,8 @@ template <int D, int DP>  // head dim and its padding to a multiple of 16
 __global__ void __launch_bounds__(128)
 attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v, int N, int H, int ld,
                  __half* __restrict__ out, int ldo, float scale_log2) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int LDQ = DP + 8, KS = DP / 16, NO = DP / 8;
   extern __shared__ __align__(16) __half smem_h[];
   __half* sQ = smem_h;
@@ -164,9 +166,9 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
     O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(160)));
     attr = true;
   }
-  if (d == 40) attention_kernel<40, 48><<<grid, 128, smem(48), st>>>(qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2);
-  else if (d == 80) attention_kernel<80, 80><<<grid, 128, smem(80), st>>>(qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2);
-  else if (d == 160) attention_kernel<160, 160><<<grid, 128, smem(160), st>>>(qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2);
+  if (d == 40) O2345_CUDA(launch_pdl(attention_kernel<40, 48>, dim3(grid), dim3(128), (size_t)(smem(48)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
+  else if (d == 80) O2345_CUDA(launch_pdl(attention_kernel<80, 80>, dim3(grid), dim3(128), (size_t)(smem(80)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
+  else if (d == 160) O2345_CUDA(launch_pdl(attention_kernel<160, 160>, dim3(grid), dim3(128), (size_t)(smem(160)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
   else { set_error("o2345_attention_f16: head dim %d not built (40 / 80 / 160)", d); return O2345_EUNSUPPORTED; }
   O2345_LAUNCH_CHECK();
   return O2345_OK;

@@ -38,4 +38,25 @@ int sm_count();
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// Programmatic dependent launch (PDL).  The ~660 kernels of a UNet pass are launched with programmatic stream
+// serialization: kernel N+1 may be scheduled while kernel N drains, runs its prologue (barrier init, TMEM allocation,
+// descriptor prefetch, index math) and then blocks in pdl_wait() until kernel N has completed and flushed its writes.
+// Every kernel launched this way calls pdl_wait() before its first access to memory another kernel may have written (or
+// may still read), so the chain stays transitively ordered; kernels launched normally are unaffected (wait is a no-op).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // api.cu: environment O2345_PDL (default on; "0" switches the launch attribute off)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace o2345

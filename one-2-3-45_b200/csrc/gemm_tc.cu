@@ -457,6 +457,8 @@ gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above touched no global memory: it overlaps the tail of the previous kernel
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
@@ -573,6 +575,8 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();   // barrier inits of the leader must be visible before the peer's TMA can complete on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above touched no global memory: it overlaps the tail of the previous kernel
+  pdl_trigger();
   if (threadIdx.x == 0) stamp(p, 1);
 
   if (warp == 0) {
@@ -679,6 +683,8 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t l
 // split-K epilogue: out = act(alpha * ws + bias + rowbias) + residual, and ws is left zeroed for the next call.
 // One thread per (row, 8 columns) when N and ldc allow 16-byte accesses, else one per element.
 __global__ void splitk_finalize_kernel(GemmParams p, int vec) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (vec) {
     const int n8 = p.N >> 3;
@@ -748,7 +754,7 @@ int finalize(const GemmParams& p, cudaStream_t st) {
   if (p.splits <= 1) return O2345_OK;
   const int vec = (p.N % 8) == 0 && (p.ldc % 8) == 0 && (!p.rowbias || (p.rowbias_ld % 8) == 0);
   const int64_t n = vec ? (int64_t)p.M * (p.N / 8) : (int64_t)p.M * p.N;
-  splitk_finalize_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, vec);
+  O2345_CUDA(launch_pdl(splitk_finalize_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), st, p, vec));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
@@ -762,7 +768,7 @@ int launch1(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int
     attr = true;
   }
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), batch > 0 ? batch : (p.splits > 1 ? p.splits : 1));
-  gemm_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SMEM, st>>>(a, b, p);
+  O2345_CUDA(launch_pdl(gemm_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), (size_t)(SMEM), st, a, b, p));
   O2345_LAUNCH_CHECK();
   return finalize(p, st);
 }
@@ -776,7 +782,7 @@ int launch2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cud
     attr = true;
   }
   dim3 grid(2 * cdiv(p.M, 2 * BM), cdiv(p.N, BN), p.splits > 1 ? p.splits : 1);
-  gemm2_f16_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SMEM, st>>>(a, b, p);
+  O2345_CUDA(launch_pdl(gemm2_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), (size_t)(SMEM), st, a, b, p));
   O2345_LAUNCH_CHECK();
   return finalize(p, st);
 }

@@ -31,6 +31,8 @@ __global__ void groupnorm_stats_kernel(const __half* __restrict__ x, int HW, int
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ scratch, int B, int P,
                                        float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float gsm[];           // [2 G] sums, then [2 G] mean / rstd
   __shared__ int is_last;
   const int b = blockIdx.y, c8n = C >> 3, cg = C / G;
@@ -93,6 +95,8 @@ __global__ void groupnorm_stats_kernel(const __half* __restrict__ x, int HW, int
 __global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int KS, int stride, int up,
                                        const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                        __half* __restrict__ out, int Ho, int Wo, int pad) {
+  pdl_wait();
+  pdl_trigger();
   const int c8 = C >> 3;  // 8 channels (16 bytes) per thread
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)B * Ho * Wo * KS * KS * c8;
@@ -134,6 +138,8 @@ __global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int 
 __global__ void layernorm_rows_kernel(const __half* __restrict__ x, int64_t M, int C, float eps,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                       __half* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -147,6 +153,8 @@ __global__ void layernorm_rows_kernel(const __half* __restrict__ x, int64_t M, i
 
 // one warp per row of length n (<= 1024): probabilities in fp16
 __global__ void softmax_rows_kernel(const __half* __restrict__ s, int64_t rows, int n, __half* __restrict__ p) {
+  pdl_wait();
+  pdl_trigger();
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -168,6 +176,8 @@ __global__ void softmax_rows_kernel(const __half* __restrict__ s, int64_t rows, 
 }
 
 __global__ void geglu_kernel(const __half* __restrict__ x, int64_t M, int I, __half* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   const int i8 = I >> 3;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * i8) return;
@@ -186,12 +196,16 @@ __global__ void geglu_kernel(const __half* __restrict__ x, int64_t M, int I, __h
 }
 
 __global__ void silu_kernel(const __half* __restrict__ x, int64_t n, __half* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = __float2half_rn(silu(__half2float(x[i])));
 }
 
 // [B, N, C] -> [B, C, N]
 __global__ void transpose_tokens_kernel(const __half* __restrict__ x, int N, int C, __half* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __half tile[32][33];
   int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -207,6 +221,8 @@ __global__ void transpose_tokens_kernel(const __half* __restrict__ x, int N, int
 
 // timestep_embedding(t, dim): [cos(t * f_i) | sin(t * f_i)], f_i = exp(-ln(10000) * i / half)   (util.py:151-171)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int half_dim = dim / 2;
   if (i >= B * half_dim) return;
@@ -219,6 +235,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
 
 // y[b, p, c] += e[b, c]   (ResBlock: h + emb_out[..., None, None], openaimodel.py:271)
 __global__ void add_channel_bias_kernel(__half* __restrict__ y, const __half* __restrict__ e, int HW, int C, int lde, int64_t total) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int c = (int)(i % C);
@@ -228,6 +246,8 @@ __global__ void add_channel_bias_kernel(__half* __restrict__ y, const __half* __
 
 // dst[:, off:off+C] = src  (channel concat on channel-last rows)
 __global__ void copy_channels_kernel(const __half* __restrict__ src, int64_t M, int C, __half* __restrict__ dst, int ldd, int off) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int c8 = C >> 3;
   if (i >= M * c8) return;
@@ -237,6 +257,8 @@ __global__ void copy_channels_kernel(const __half* __restrict__ src, int64_t M, 
 }
 
 __global__ void nchw_f32_to_cl_f16_kernel(const float* __restrict__ x, int B, int C, int HW, __half* __restrict__ y, int ldy, int off) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * C * HW) return;
   int p = (int)(i % HW), c = (int)((i / HW) % C);
@@ -245,6 +267,8 @@ __global__ void nchw_f32_to_cl_f16_kernel(const float* __restrict__ x, int B, in
 }
 
 __global__ void cl_f16_to_nchw_f32_kernel(const __half* __restrict__ x, int B, int C, int HW, int ldx, float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * C * HW) return;
   int p = (int)(i % HW), c = (int)((i / HW) % C);
@@ -257,6 +281,8 @@ __global__ void cl_f16_to_nchw_f32_kernel(const __half* __restrict__ x, int B, i
 __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
                                        int64_t n, float scale, float a_t, float a_prev, float sigma_t, float sqrt_1m_at,
                                        float* __restrict__ x_prev, float* __restrict__ pred_x0) {
+  pdl_wait();
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float eu = eps[i], ec = eps[n + i];
@@ -288,8 +314,8 @@ extern "C" int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G,
   if (chunks < 1) chunks = 1;
   const int P = cdiv(HW, chunks);
   chunks = cdiv(HW, P);
-  groupnorm_stats_kernel<<<dim3(chunks, B), threads, 4 * G * sizeof(float), ST>>>((const __half*)x, HW, C, G, eps, gamma, beta,
-                                                                                  scratch, B, P, scale, shift);
+  O2345_CUDA(launch_pdl(groupnorm_stats_kernel, dim3(dim3(chunks, B)), dim3(threads), (size_t)(4 * G * sizeof(float)), ST, (const __half*)x, HW, C, G, eps, gamma, beta,
+                                                                                  scratch, B, P, scale, shift));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
@@ -302,8 +328,8 @@ extern "C" int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, 
   int pad_hi = ksize / 2, pad = pad_lo < 0 ? ksize / 2 : pad_lo;   // pad_lo = 0: the VAE's (0,1,0,1) down-sampling pad
   int Ho = (Hin + pad + pad_hi - ksize) / stride + 1, Wo = (Win + pad + pad_hi - ksize) / stride + 1;
   int64_t total = (int64_t)B * Ho * Wo * ksize * ksize * (C / 8);
-  norm_act_im2col_kernel<<<cdiv(total, 256), 256, 0, ST>>>((const __half*)x, B, H, W, C, ksize, stride, upsample, scale, shift,
-                                                           act, (__half*)out, Ho, Wo, pad);
+  O2345_CUDA(launch_pdl(norm_act_im2col_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), ST, (const __half*)x, B, H, W, C, ksize, stride, upsample, scale, shift,
+                                                           act, (__half*)out, Ho, Wo, pad));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
@@ -311,42 +337,42 @@ extern "C" int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, 
 extern "C" int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,
                                     o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y && gamma && beta, "null pointer");
-  layernorm_rows_kernel<<<cdiv(M, 8), 256, 0, ST>>>((const __half*)x, M, C, eps, gamma, beta, (__half*)y);
+  O2345_CUDA(launch_pdl(layernorm_rows_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)(0), ST, (const __half*)x, M, C, eps, gamma, beta, (__half*)y));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream) {
   O2345_CHECK_ARG(s && p && n >= 1 && n <= 1024, "row length must be 1..1024");
-  softmax_rows_kernel<<<cdiv(rows, 8), 256, 0, ST>>>((const __half*)s, rows, n, (__half*)p);
+  O2345_CUDA(launch_pdl(softmax_rows_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)(0), ST, (const __half*)s, rows, n, (__half*)p));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_geglu(const void* x, int64_t M, int I, void* y, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y && (I % 8) == 0, "null pointer / I must be a multiple of 8");
-  geglu_kernel<<<cdiv(M * (I / 8), 256), 256, 0, ST>>>((const __half*)x, M, I, (__half*)y);
+  O2345_CUDA(launch_pdl(geglu_kernel, dim3(cdiv(M * (I / 8), 256)), dim3(256), (size_t)(0), ST, (const __half*)x, M, I, (__half*)y));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_silu(const void* x, int64_t n, void* y, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y, "null pointer");
-  silu_kernel<<<cdiv(n, 256), 256, 0, ST>>>((const __half*)x, n, (__half*)y);
+  O2345_CUDA(launch_pdl(silu_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), ST, (const __half*)x, n, (__half*)y));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_transpose_tokens(const void* x, int B, int N, int C, void* y, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y, "null pointer");
-  transpose_tokens_kernel<<<dim3(cdiv(N, 32), cdiv(C, 32), B), dim3(32, 8), 0, ST>>>((const __half*)x, N, C, (__half*)y);
+  O2345_CUDA(launch_pdl(transpose_tokens_kernel, dim3(dim3(cdiv(N, 32), cdiv(C, 32), B)), dim3(dim3(32, 8)), (size_t)(0), ST, (const __half*)x, N, C, (__half*)y));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_timestep_embedding(const float* t, int B, int dim, void* out, o2345_stream_t stream) {
   O2345_CHECK_ARG(t && out && dim % 2 == 0, "bad arguments");
-  timestep_embedding_kernel<<<cdiv(B * dim / 2, 128), 128, 0, ST>>>(t, B, dim, (__half*)out);
+  O2345_CUDA(launch_pdl(timestep_embedding_kernel, dim3(cdiv(B * dim / 2, 128)), dim3(128), (size_t)(0), ST, t, B, dim, (__half*)out));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
@@ -354,28 +380,28 @@ extern "C" int o2345_timestep_embedding(const float* t, int B, int dim, void* ou
 extern "C" int o2345_add_channel_bias(void* y, const void* e, int B, int HW, int C, int lde, o2345_stream_t stream) {
   O2345_CHECK_ARG(y && e, "null pointer");
   int64_t total = (int64_t)B * HW * C;
-  add_channel_bias_kernel<<<cdiv(total, 256), 256, 0, ST>>>((__half*)y, (const __half*)e, HW, C, lde, total);
+  O2345_CUDA(launch_pdl(add_channel_bias_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), ST, (__half*)y, (const __half*)e, HW, C, lde, total));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_copy_channels(const void* src, int64_t M, int C, void* dst, int ldd, int off, o2345_stream_t stream) {
   O2345_CHECK_ARG(src && dst && (C % 8) == 0 && (ldd % 8) == 0 && (off % 8) == 0, "channels must be multiples of 8");
-  copy_channels_kernel<<<cdiv(M * (C / 8), 256), 256, 0, ST>>>((const __half*)src, M, C, (__half*)dst, ldd, off);
+  O2345_CUDA(launch_pdl(copy_channels_kernel, dim3(cdiv(M * (C / 8), 256)), dim3(256), (size_t)(0), ST, (const __half*)src, M, C, (__half*)dst, ldd, off));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_nchw_f32_to_cl_f16(const float* x, int B, int C, int HW, void* y, int ldy, int off, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y, "null pointer");
-  nchw_f32_to_cl_f16_kernel<<<cdiv((int64_t)B * C * HW, 256), 256, 0, ST>>>(x, B, C, HW, (__half*)y, ldy, off);
+  O2345_CUDA(launch_pdl(nchw_f32_to_cl_f16_kernel, dim3(cdiv((int64_t)B * C * HW, 256)), dim3(256), (size_t)(0), ST, x, B, C, HW, (__half*)y, ldy, off));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
 
 extern "C" int o2345_cl_f16_to_nchw_f32(const void* x, int B, int C, int HW, int ldx, float* y, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y, "null pointer");
-  cl_f16_to_nchw_f32_kernel<<<cdiv((int64_t)B * C * HW, 256), 256, 0, ST>>>((const __half*)x, B, C, HW, ldx, y);
+  O2345_CUDA(launch_pdl(cl_f16_to_nchw_f32_kernel, dim3(cdiv((int64_t)B * C * HW, 256)), dim3(256), (size_t)(0), ST, (const __half*)x, B, C, HW, ldx, y));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
@@ -384,7 +410,7 @@ extern "C" int o2345_cfg_ddim_update(const float* x, const float* eps, const flo
                                      float a_prev, float sigma_t, float sqrt_one_minus_at, float* x_prev, float* pred_x0,
                                      o2345_stream_t stream) {
   O2345_CHECK_ARG(x && eps && x_prev, "null pointer");
-  cfg_ddim_update_kernel<<<cdiv(n, 256), 256, 0, ST>>>(x, eps, noise, n, scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, x_prev, pred_x0);
+  O2345_CUDA(launch_pdl(cfg_ddim_update_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), ST, x, eps, noise, n, scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, x_prev, pred_x0));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
