@@ -287,18 +287,27 @@ def render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk):
     ms_sdf = float(np.mean([ev_time(f_sdf)[0] for _ in range(3)]))
     views = tr.sdf_renderer_lod0._source_views(fmaps, imgs, sample['w2cs'][0], sample['intrinsics'][0], [sizeW, sizeH])
     qc = ops.cf32(sample['query_c2w'].reshape(-1, 4, 4)[0, :3, 3])
-    f_bl = lambda: ops.render_blend(src, active, vol_cl, occ, views, tr.rendering_network_lod0.packed(), query_center=qc)
+    prec = tr.sdf_renderer_lod0.blend_precision
+    f_bl = lambda: ops.render_blend(src, active, vol_cl, occ, views, tr.rendering_network_lod0.packed(), query_center=qc,
+                                    precision=prec)
     f_bl()
     ms_bl = float(np.mean([ev_time(f_bl)[0] for _ in range(3)]))
     pairs = int(f_bl()[1].sum())
+    f_bl32 = lambda: ops.render_blend(src, active, vol_cl, occ, views, tr.rendering_network_lod0.packed(), query_center=qc,
+                                      precision=0)
+    rgb32 = f_bl32()[0]
+    ms_bl32 = float(np.mean([ev_time(f_bl32)[0] for _ in range(2)]))
+    drift = float((f_bl()[0] - rgb32).abs().max())
     t_roof = max(RAY_FLOP / (pk["bf16_tflops"] * 1e12), RAY_GATHER_BYTES / (pk["hbm_gbs"] * 1e9)) * N_RAYS
     return {"metric": "volume-render M rays/sec", "value": N_RAYS / (ms_img * 1e-3) / 1e6, "unit": "M rays/s",
-            "workload": "65536 rays x (64+64) samples x 32 views, fp32, volume + feature maps resident",
+            "workload": "65536 rays x (64+64) samples x 32 views, volume + feature maps resident; SDF MLP fp32, view-blending "
+                        "MLPs on tensor cores (fp16 operands, fp32 accumulate / statistics)",
             "image_ms": ms_img, "frac_of_survey_contract": t_roof * 1e3 / ms_img,
             "kernels_first_chunk": {
                 "sdf_query_kernel<grad>": {"ms": ms_sdf, "tflops": n_act * (FLOP_SDF_FWD + FLOP_SDF_BWD) / (ms_sdf * 1e-3) / 1e12,
                                            "active_samples": n_act},
-                "render_blend_kernel": {"ms": ms_bl, "valid_pairs": pairs,
+                "render_blend_tc_kernel": {"ms": ms_bl, "valid_pairs": pairs, "ms_fp32_kernel": ms_bl32,
+                                           "max_colour_drift_vs_fp32_kernel": drift,
                                         "gather_gbs": (pairs * 960 + n_act * 544) / (ms_bl * 1e-3) / 1e9}}}
 
 
