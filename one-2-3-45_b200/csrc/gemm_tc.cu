@@ -20,6 +20,7 @@
 // Two pairs are co-resident per SM pair (<= 104 KB smem, <= 256 TMEM columns each), so one tile's prologue / epilogue
 // overlaps the other's main loop.  The single-CTA kernel (gemm1) remains for N <= 64 and for the 4-D batched (per-head) mode.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -734,11 +735,17 @@ __global__ void splitk_finalize_kernel(GemmParams p, int vec) {
 // how many k-splits for a non-batched problem whose output tiles give `ctas` CTAs: fill ~2 CTAs per SM, keep >= 4 k-blocks
 // per split
 int pick_splits(const GemmParams& p, int ctas, float* ws, int64_t ws_floats) {
+  static int min_kb = -1;
+  if (min_kb < 0) {   // k-blocks each split must keep (tuning knob; the default is the measured optimum of the UNet pass)
+    const char* e = getenv("O2345_SPLITK_MIN_KB");
+    min_kb = e ? atoi(e) : 12;   // r1 sweep of the UNet pass: 4 -> 5.20 ms, 8 -> 5.03, 12 -> 4.98, 16 -> 5.01, 24 -> 5.11
+    if (min_kb < 1) min_kb = 1;
+  }
   if (!ws || p.batched || p.act == 3 || (int64_t)p.M * p.N > ws_floats) return 1;
   int nk = p.conv ? 9 * p.cblocks : cdiv(p.K, BK);
-  if (ctas >= 120 || nk < 16) return 1;
+  if (ctas >= 120 || nk < 2 * min_kb) return 1;
   int s = 2 * sm_count() / ctas;
-  if (s > nk / 4) s = nk / 4;
+  if (s > nk / min_kb) s = nk / min_kb;
   if (s > 32) s = 32;
   return s < 2 ? 1 : s;
 }
