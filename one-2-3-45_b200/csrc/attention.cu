@@ -155,6 +155,7 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
                                    int ldo, float scale, o2345_stream_t stream) {
   O2345_CHECK_ARG(q && k && v && out, "null pointer");
   O2345_CHECK_ARG(B > 0 && N > 0 && H > 0 && (ld % 8) == 0 && (ldo % 2) == 0, "bad sizes");
+  O2345_CHECK_ARG(d == 40 || d == 80 || d == 160, "head dim must be 40, 80 or 160");
   O2345_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0, "q/k/v must be 16-byte aligned");
   dim3 grid(cdiv(N, QT), B * H);
   float sl2 = scale * 1.4426950408889634f;
