@@ -120,8 +120,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"             # keep NCCL's version banner off stdout: ONE JSON line is the contract
+        # keep NCCL's version banner / warnings off stdout: ONE JSON line is the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     tr = build_networks(dev, vol_dim=VOL, states=S.all_states(0), perturb=0.0)
     z123 = build_zero123(dev, seed=0).half()            # `--half_precision`: fp16-rounded schedule buffers
