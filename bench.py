@@ -165,7 +165,7 @@ def run_gpu(args):
         out.update(stage_breakdown(z123, tr, dev, pk))
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference()
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -364,14 +364,29 @@ def run_reference(args):
     if int(os.environ.get("RANK", 0)) != 0:
         return
     cb = cpu_reference()
-    print(json.dumps({"impl": "reference", "metric": "sec/mesh end-to-end (256x256 in)", "value": cb["value"], "unit": "s/mesh",
+    emit(json.dumps({"impl": "reference", "metric": "sec/mesh end-to-end (256x256 in)", "value": cb["value"], "unit": "s/mesh",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["value"] * 1e3,
                       "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": CONFIG, "cpu_baseline": cb,
-                      "e2e": {"value": cb["value"], "unit": "s/mesh", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                      "e2e": {"value": cb["value"], "unit": "s/mesh", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else printed to fd 1 (NCCL's version banner,
+    library chatter) has been re-routed to stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
