@@ -90,8 +90,11 @@ typedef struct o2345_points {
  *         sparse_neus_renderer.py:135-139, 229-241).
  * Outputs (any may be NULL): sdf [n], feat [n,127], latent [n,16], grad [n,3].
  * If negate != 0 the sdf output is written as -sdf (extract_fields' u = -sdf). */
+#define O2345_SDF_FP32 0      /* fp32 FMA GEMMs                                                                        */
+#define O2345_SDF_TC_SPLIT 1  /* forward GEMMs on tensor cores, every operand split into fp16 hi + lo (three MMAs per
+                                 product, fp32 accumulate): agrees with the fp32 kernel to ~1e-6                         */
 int o2345_sdf_query(const o2345_points* src, int64_t n, const float* vol_cl, int D, const float* wpack,
-                    const uint8_t* active, float inactive_sdf, int negate, float* sdf, float* feat,
+                    const uint8_t* active, float inactive_sdf, int negate, int precision, float* sdf, float* feat,
                     float* latent, float* grad, o2345_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

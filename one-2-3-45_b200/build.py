@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libo2345_sm100.so")
-SOURCES = ["api.cu", "sdf_mlp.cu", "costvol.cu", "spconv.cu", "mcubes.cu", "featnet.cu", "render.cu", "render_tc.cu", "gemm_tc.cu", "unet_ops.cu", "attention.cu"]
+SOURCES = ["api.cu", "sdf_mlp.cu", "costvol.cu", "spconv.cu", "mcubes.cu", "featnet.cu", "render.cu", "render_tc.cu", "sdf_mlp_tc.cu", "gemm_tc.cu", "unet_ops.cu", "attention.cu"]
 # no --use_fast_math: parity with the fp32 reference comes first
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

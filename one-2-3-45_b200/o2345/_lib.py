@@ -36,6 +36,7 @@ class Epilogue(C.Structure):
 
 PTS_EXPLICIT, PTS_LATTICE, PTS_RAYS = 0, 1, 2
 BLEND_FP32, BLEND_TC_FP16 = 0, 1
+SDF_FP32, SDF_TC_SPLIT = 0, 1
 SDF_PACK_FLOATS = 39 * 128 + 128 + 2 * (144 * 128 + 128) + 128 * 144 + 128 * 48
 RNET_PACK_FLOATS = 19664
 MAP_CH = 60
@@ -45,7 +46,7 @@ _SIGS = {
     "o2345_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
     "o2345_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "o2345_sdf_pack_weights": (C.c_int, [c_fp] * 7 + [c_fp]),
-    "o2345_sdf_query": (C.c_int, [C.POINTER(Points), c_i64, c_fp, C.c_int, c_fp, c_fp, C.c_float, C.c_int,
+    "o2345_sdf_query": (C.c_int, [C.POINTER(Points), c_i64, c_fp, C.c_int, c_fp, c_fp, C.c_float, C.c_int, C.c_int,
                                   c_fp, c_fp, c_fp, c_fp, c_fp]),
     "o2345_frustum_mask": (C.c_int, [c_fp, C.c_int, c_fp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, c_fp,
                                      c_fp, c_fp]),

@@ -78,9 +78,15 @@ def sdf_pack_weights(w0, b0, w1, b1, w2, b2):
     return pack
 
 
+# SDF MLP kernel used when a call does not say otherwise: forward GEMMs on tensor cores with split-fp16 operands
+# (fp32-grade values); L.SDF_FP32 selects the fp32 FMA kernel.
+SDF_PRECISION = L.SDF_TC_SPLIT
+
+
 def sdf_query(src: PointSource, vol_cl, pack, active=None, inactive_sdf=100.0, negate=False, want_feat=False,
-              want_latent=False, want_grad=False):
+              want_latent=False, want_grad=False, precision=None):
     """Returns dict(sdf [n,1], feat [n,127]?, latent [n,16]?, grad [n,3]?)."""
+    precision = SDF_PRECISION if precision is None else precision
     n, dev = src.n, vol_cl.device
     D = vol_cl.shape[0]
     out = {"sdf": torch.empty(n, 1, dtype=_f32, device=dev)}
@@ -91,7 +97,7 @@ def sdf_query(src: PointSource, vol_cl, pack, active=None, inactive_sdf=100.0, n
     if want_grad:
         out["grad"] = torch.empty(n, 3, dtype=_f32, device=dev)
     L.call("o2345_sdf_query", C.byref(src.struct), n, _f(vol_cl), D, _f(pack), _p(active, _u8),
-           float(inactive_sdf), int(bool(negate)), _f(out["sdf"]), _f(out.get("feat")), _f(out.get("latent")),
+           float(inactive_sdf), int(bool(negate)), int(precision), _f(out["sdf"]), _f(out.get("feat")), _f(out.get("latent")),
            _f(out.get("grad")), _stream())
     return out
 
