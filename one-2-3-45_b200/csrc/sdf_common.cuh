@@ -36,6 +36,21 @@ __device__ __forceinline__ float softplus100(float x) {
 // d softplus / dx expressed through the activation a = softplus(x): sigmoid(100x) = 1 - exp(-100a)
 __device__ __forceinline__ float dsoftplus_from_act(float a) { return -expm1f(-100.f * a); }
 
+// MUFU versions for the tensor-core kernel (ex2 / lg2 approximations: absolute error < 2e-7 on activations of O(1),
+// below that kernel's 2e-6 agreement with the fp32 one; the precise log1pf / expf / expm1f cost ~80 instructions each)
+__device__ __forceinline__ float softplus100_fast(float x) {
+  const float bx = 100.f * x;
+  float e, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(bx * 1.4426950408889634f));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
+  return bx > 20.f ? x : l * (0.6931471805599453f * 0.01f);
+}
+__device__ __forceinline__ float dsoftplus_from_act_fast(float a) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-144.26950408889634f * a));
+  return 1.f - e;
+}
+
 struct Tri {
   int base[3];     // clamped floor index per axis (x,y,z)
   int hi[3];       // clamped floor+1 index
@@ -123,6 +138,7 @@ __device__ __forceinline__ void gemm_bwd(const float* __restrict__ sA, const flo
 }
 
 __device__ __forceinline__ void load_weights(float* sW, const float* __restrict__ g, int nfloats) {
+#pragma unroll 6   // several independent L2 loads in flight
   for (int i = threadIdx.x * 4; i < nfloats; i += NT * 4)
     *reinterpret_cast<float4*>(sW + i) = ldg4(g + i);
 }
@@ -130,6 +146,7 @@ __device__ __forceinline__ void load_weights(float* sW, const float* __restrict_
 // Reverse pass from delta1 = d sdf / d z1 (fp32, sAct rows 0..127, k-major [feature][point]) to d sdf / d xyz:
 // two transposed GEMMs (W1, W0), the softplus derivative of layer 0 (activations in sA0), then per point the embedding
 // and trilinear contractions.  Shared by both SDF kernels; every thread of the CTA must call it.
+template <bool FAST = false>
 __device__ __forceinline__ void backward_from_delta1(float* sAct, float* sW, float* sA0, const float* sPts, float* sGp,
                                                      const int* sFlag, const float* __restrict__ wp,
                                                      const float* __restrict__ vol, int D, int64_t gi, int64_t n,
@@ -157,7 +174,7 @@ __device__ __forceinline__ void backward_from_delta1(float* sAct, float* sW, flo
         float4 a1 = *reinterpret_cast<const float4*>(sA0 + nn * TM + m0 + 4);
         float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = g[i][j] * dsoftplus_from_act(a[i]);
+        for (int i = 0; i < 8; ++i) v[i] = g[i][j] * (FAST ? dsoftplus_from_act_fast(a[i]) : dsoftplus_from_act(a[i]));
       } else {      // gradient w.r.t. the latent: direct path through layer 2 + layer 1
         float w = __ldg(wp + OFF_W2T + nn * HID);
 #pragma unroll

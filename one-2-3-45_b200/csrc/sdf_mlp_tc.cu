@@ -56,6 +56,7 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 
 // weights of one layer: fp32 [K][128] (k-major, as packed) -> hi / lo planes [KP][LDP]; rows K..KP-1 are zero
 __device__ __forceinline__ void load_weight_planes(__half* sWh, __half* sWl, const float* __restrict__ g, int K, int KP) {
+#pragma unroll 6   // several independent L2 loads in flight (18 trips for a 144-row layer)
   for (int i = threadIdx.x * 4; i < KP * HID; i += NT * 4) {
     const int k = i >> 7, c = i & 127;
     float4 v = k < K ? ldg4(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -123,7 +124,7 @@ __device__ __forceinline__ void store_activations(float (&acc)[2][8][4], __half*
 #pragma unroll
       for (int q = 0; q < 4; ++q) {           // q = 2 * (n-tile of the pair) + (row half): blocks (m lo, n0), (m hi, n0), (m lo, n1), (m hi, n1)
         const int j = 2 * np + (q >> 1), r = q & 1;
-        const float v0 = softplus100(acc[mt][j][2 * r]), v1 = softplus100(acc[mt][j][2 * r + 1]);
+        const float v0 = softplus100_fast(acc[mt][j][2 * r]), v1 = softplus100_fast(acc[mt][j][2 * r + 1]);
         if (sA0) {
           const int m = mw + 16 * mt + 8 * r + g, nn = nw + 8 * j + 2 * t;
           sA0[nn * TM + m] = v0, sA0[(nn + 1) * TM + m] = v1;
@@ -297,12 +298,12 @@ sdf_query_tc_kernel(o2345_points src, int64_t n, const float* __restrict__ vol, 
       for (int i = 0; i < HID * TM / NT; ++i) {
         const int e = tid + i * NT, j = e >> 7, m = e & (TM - 1);
         const float a1 = __half2float(sAh[j * LDP + m]) + __half2float(sAl[j * LDP + m]);
-        d[i] = __ldg(wp + OFF_W2T + j * HID) * dsoftplus_from_act(a1);
+        d[i] = __ldg(wp + OFF_W2T + j * HID) * dsoftplus_from_act_fast(a1);
       }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < HID * TM / NT; ++i) sAct[tid + i * NT] = d[i];
-      backward_from_delta1(sAct, sW, sA0, sPts, sGp, sFlag, wp, vol, D, gi, n, o_grad);
+      backward_from_delta1<true>(sAct, sW, sA0, sPts, sGp, sFlag, wp, vol, D, gi, n, o_grad);
     }
     __syncthreads();  // smem is reused by the next tile
   }
