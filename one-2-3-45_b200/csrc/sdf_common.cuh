@@ -143,6 +143,70 @@ __device__ __forceinline__ void load_weights(float* sW, const float* __restrict_
     *reinterpret_cast<float4*>(sW + i) = ldg4(g + i);
 }
 
+// Last step of the reverse pass, per point: contraction of d sdf / d PE (sGpe [48][TM]) with d PE / d xyz (threads
+// 0..127) and of d sdf / d latent (sGlat [16][TM]) with the derivative of the trilinear weights (threads 128..255).
+__device__ __forceinline__ void backward_point_tail(const float* sGpe, const float* sGlat, const float* sPts, float* sGp,
+                                                    const int* sFlag, const float* __restrict__ vol, int D, int64_t gi,
+                                                    int64_t n, float* __restrict__ o_grad) {
+  const int tid = threadIdx.x;
+  const int pm = tid & (TM - 1), half = tid >> 7;
+  // ---------------- per point: embedding part (half 0) + trilinear part (half 1) ---
+  {
+    float qx = sPts[pm], qy = sPts[TM + pm], qz = sPts[2 * TM + pm];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (half == 0) {
+      float p[3] = {qx, qy, qz};
+      float gg[3] = {sGpe[0 * TM + pm], sGpe[1 * TM + pm], sGpe[2 * TM + pm]};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        float fr = (float)(1 << k);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          float s, c;
+          sincosf(fr * p[a], &s, &c);
+          float gs = sGpe[(3 + 6 * k + a) * TM + pm], gc = sGpe[(3 + 6 * k + 3 + a) * TM + pm];
+          gg[a] = fmaf(fr, gs * c - gc * s, gg[a]);
+        }
+      }
+      gx = gg[0], gy = gg[1], gz = gg[2];
+    } else {
+      Tri t = tri_setup(qx, qy, qz, D);
+      if (t.inb) {
+        float gl[LAT];
+#pragma unroll
+        for (int c = 0; c < LAT; ++c) gl[c] = sGlat[c * TM + pm];
+        float sc = 0.5f * (float)(D - 1);  // d t / d p
+#pragma unroll
+        for (int corner = 0; corner < 8; ++corner) {
+          int dx = corner >> 2, dy = (corner >> 1) & 1, dz = corner & 1;
+          int ix = dx ? t.hi[0] : t.base[0], iy = dy ? t.hi[1] : t.base[1], iz = dz ? t.hi[2] : t.base[2];
+          const float* v = vol + (((int64_t)ix * D + iy) * D + iz) * LAT;
+          float dot = 0.f;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            float4 vv = ldg4(v + 4 * c4);
+            dot = fmaf(vv.x, gl[4 * c4], dot); dot = fmaf(vv.y, gl[4 * c4 + 1], dot);
+            dot = fmaf(vv.z, gl[4 * c4 + 2], dot); dot = fmaf(vv.w, gl[4 * c4 + 3], dot);
+          }
+          float wx = dx ? t.w1[0] : t.w0[0], wy = dy ? t.w1[1] : t.w0[1], wz = dz ? t.w1[2] : t.w0[2];
+          float sx = dx ? sc : -sc, sy = dy ? sc : -sc, sz = dz ? sc : -sc;
+          gx = fmaf(dot, sx * wy * wz, gx);
+          gy = fmaf(dot, wx * sy * wz, gy);
+          gz = fmaf(dot, wx * wy * sz, gz);
+        }
+      }
+      sGp[pm] = gx, sGp[TM + pm] = gy, sGp[2 * TM + pm] = gz;
+    }
+    __syncthreads();
+    if (half == 0 && gi < n && o_grad) {
+      bool on = sFlag[pm] != 0;
+      o_grad[3 * gi] = on ? gx + sGp[pm] : 0.f;
+      o_grad[3 * gi + 1] = on ? gy + sGp[TM + pm] : 0.f;
+      o_grad[3 * gi + 2] = on ? gz + sGp[2 * TM + pm] : 0.f;
+    }
+  }
+}
+
 // Reverse pass from delta1 = d sdf / d z1 (fp32, sAct rows 0..127, k-major [feature][point]) to d sdf / d xyz:
 // two transposed GEMMs (W1, W0), the softplus derivative of layer 0 (activations in sA0), then per point the embedding
 // and trilinear contractions.  Shared by both SDF kernels; every thread of the CTA must call it.
@@ -202,61 +266,7 @@ __device__ __forceinline__ void backward_from_delta1(float* sAct, float* sW, flo
     }
   }
   __syncthreads();
-  // ---------------- per point: embedding part (half 0) + trilinear part (half 1) ---
-  {
-    float qx = sPts[pm], qy = sPts[TM + pm], qz = sPts[2 * TM + pm];
-    float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (half == 0) {
-      float p[3] = {qx, qy, qz};
-      float gg[3] = {sA0[0 * TM + pm], sA0[1 * TM + pm], sA0[2 * TM + pm]};
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        float fr = (float)(1 << k);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          float s, c;
-          sincosf(fr * p[a], &s, &c);
-          float gs = sA0[(3 + 6 * k + a) * TM + pm], gc = sA0[(3 + 6 * k + 3 + a) * TM + pm];
-          gg[a] = fmaf(fr, gs * c - gc * s, gg[a]);
-        }
-      }
-      gx = gg[0], gy = gg[1], gz = gg[2];
-    } else {
-      Tri t = tri_setup(qx, qy, qz, D);
-      if (t.inb) {
-        float gl[LAT];
-#pragma unroll
-        for (int c = 0; c < LAT; ++c) gl[c] = sAct[(HID + c) * TM + pm];
-        float sc = 0.5f * (float)(D - 1);  // d t / d p
-#pragma unroll
-        for (int corner = 0; corner < 8; ++corner) {
-          int dx = corner >> 2, dy = (corner >> 1) & 1, dz = corner & 1;
-          int ix = dx ? t.hi[0] : t.base[0], iy = dy ? t.hi[1] : t.base[1], iz = dz ? t.hi[2] : t.base[2];
-          const float* v = vol + (((int64_t)ix * D + iy) * D + iz) * LAT;
-          float dot = 0.f;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            float4 vv = ldg4(v + 4 * c4);
-            dot = fmaf(vv.x, gl[4 * c4], dot); dot = fmaf(vv.y, gl[4 * c4 + 1], dot);
-            dot = fmaf(vv.z, gl[4 * c4 + 2], dot); dot = fmaf(vv.w, gl[4 * c4 + 3], dot);
-          }
-          float wx = dx ? t.w1[0] : t.w0[0], wy = dy ? t.w1[1] : t.w0[1], wz = dz ? t.w1[2] : t.w0[2];
-          float sx = dx ? sc : -sc, sy = dy ? sc : -sc, sz = dz ? sc : -sc;
-          gx = fmaf(dot, sx * wy * wz, gx);
-          gy = fmaf(dot, wx * sy * wz, gy);
-          gz = fmaf(dot, wx * wy * sz, gz);
-        }
-      }
-      sGp[pm] = gx, sGp[TM + pm] = gy, sGp[2 * TM + pm] = gz;
-    }
-    __syncthreads();
-    if (half == 0 && gi < n && o_grad) {
-      bool on = sFlag[pm] != 0;
-      o_grad[3 * gi] = on ? gx + sGp[pm] : 0.f;
-      o_grad[3 * gi + 1] = on ? gy + sGp[TM + pm] : 0.f;
-      o_grad[3 * gi + 2] = on ? gz + sGp[2 * TM + pm] : 0.f;
-    }
-  }
+  backward_point_tail(sA0, sAct + HID * TM, sPts, sGp, sFlag, vol, D, gi, n, o_grad);
 }
 
 }  // namespace sdfk

@@ -12,7 +12,8 @@
 //          go back with stmatrix.trans; 136-half rows make every ldmatrix / stmatrix phase conflict free;
 //   warps  4 (m) x 2 (n): a warp owns 32 points x 64 outputs = 2 x 8 accumulator tiles;
 //   rest   stage 0 (trilinear latent fetch, positional embedding), the sdf-only dot product, output staging and the
-//          reverse pass (backward_from_delta1, fp32 FMA) are the code of the fp32 kernel.
+//          per-point tail of the reverse pass are the code of the fp32 kernel; the two transposed GEMMs of the
+//          reverse pass use the same split-fp16 MMAs with one 16-point m-tile per warp.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -25,7 +26,7 @@ using namespace sdfk;
 constexpr int LDP = TM + 8;                    // halves per plane row
 constexpr int PLANE = IN1 * LDP;               // halves per plane (144 rows)
 constexpr int REGION = 2 * PLANE * 2;          // bytes of a hi + lo plane pair = 78 336 >= 73 728 (an fp32 [144][128] block)
-static_assert(REGION >= SM_ACT * 4 && REGION >= SM_W * 4 && REGION >= TM * 129 * 4, "fp32 views must fit in the plane regions");
+static_assert(REGION >= TM * 129 * 4, "the fp32 output staging must fit in the weight region");
 constexpr int SMEM_TC_FWD = 2 * REGION + SM_MISC * 4;
 constexpr int SMEM_TC_GRAD = 2 * REGION + SM_A0 * 4 + SM_MISC * 4;
 constexpr int K0PAD = 48;                      // layer-0 K (39) padded to three k-blocks
@@ -102,6 +103,51 @@ __device__ __forceinline__ void gemm_split(float (&acc)[2][8][4], const __half* 
   }
 }
 
+// reverse-pass weights: fp32 [K][ncols] rows of length src_ld (k-major: W1 as [j][i], W0 as [n][i]) -> planes [K][LD]
+__device__ __forceinline__ void load_planes_generic(__half* sWh, __half* sWl, const float* __restrict__ g, int K, int ncols, int src_ld,
+                                                    int LD) {
+  const int c4n = ncols >> 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < K * c4n; i += NT) {
+    const int k = i / c4n, c = (i - k * c4n) * 4;
+    float4 v = ldg4(g + k * src_ld + c);
+    __half h[4], l[4];
+    split(v.x, h[0], l[0]), split(v.y, h[1], l[1]), split(v.z, h[2], l[2]), split(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(sWh + k * LD + c) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(sWl + k * LD + c) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  }
+}
+
+// acc[NP pairs of n-tiles] += A[16 points (columns m0..m0+15 of the planes) x 128] . W[128 x 16 NP], split-fp16.
+// One m-tile per warp: a warp reads and (in the callers) rewrites only ITS 16 point columns of the activation planes,
+// so the reverse pass needs no CTA barrier around its in-place updates.
+template <int NP>
+__device__ __forceinline__ void gemm_split_rows(float (&acc)[2 * NP][4], const __half* sAh, const __half* sAl, const __half* sWh,
+                                                const __half* sWl, int LDW, int m0, int lane) {
+  const int a_row = (lane & 7) + ((lane >> 4) & 1) * 8, a_col = ((lane >> 3) & 1) * 8;
+  const int b_row = (lane & 7) + ((lane >> 3) & 1) * 8, b_col = ((lane >> 4) & 1) * 8;
+#pragma unroll 1
+  for (int kb = 0; kb < HID / 16; ++kb) {
+    uint32_t ah[4], al[4];
+    const int offa = (16 * kb + a_row) * LDP + m0 + a_col;
+    ldsm4t(ah, sAh + offa);
+    ldsm4t(al, sAl + offa);
+#pragma unroll
+    for (int np = 0; np < NP; ++np) {
+      uint32_t bh[4], bl[4];
+      const int off = (16 * kb + b_row) * LDW + 16 * np + b_col;
+      ldsm4t(bh, sWh + off);
+      ldsm4t(bl, sWl + off);
+      mma16816(acc[2 * np], al, bh[0], bh[1]);
+      mma16816(acc[2 * np], ah, bl[0], bl[1]);
+      mma16816(acc[2 * np], ah, bh[0], bh[1]);
+      mma16816(acc[2 * np + 1], al, bh[2], bh[3]);
+      mma16816(acc[2 * np + 1], ah, bl[2], bl[3]);
+      mma16816(acc[2 * np + 1], ah, bh[2], bh[3]);
+    }
+  }
+}
+
 __device__ __forceinline__ void init_bias(float (&acc)[2][8][4], const float* __restrict__ b, int nw, int t) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -152,7 +198,6 @@ sdf_query_tc_kernel(o2345_points src, int64_t n, const float* __restrict__ vol, 
   __half* sAl = sAh + PLANE;
   __half* sWh = reinterpret_cast<__half*>(smem_raw + REGION);
   __half* sWl = sWh + PLANE;
-  float* sAct = reinterpret_cast<float*>(smem_raw);            // fp32 view of the activation region (reverse pass)
   float* sW = reinterpret_cast<float*>(smem_raw + REGION);     // fp32 view of the weight region (staging / reverse pass)
   float* sA0 = reinterpret_cast<float*>(smem_raw + 2 * REGION);
   float* sMisc = GRAD ? sA0 + SM_A0 : sA0;
@@ -289,21 +334,83 @@ sdf_query_tc_kernel(o2345_points src, int64_t n, const float* __restrict__ vol, 
       if (gi < n && o_sdf) o_sdf[gi] = sFlag[pm] ? sign * s : inactive_sdf;
     }
     if (GRAD) {
-      // ---------------- reverse pass: delta1 = W2[0][:] * softplus'(z1) as fp32 [128][TM] over the activation region,
-      //                  then the fp32 code of the FMA kernel.  The fp32 rows overlap the half planes, so every thread
-      //                  first pulls its elements into registers.
-      __syncthreads();
-      float d[HID * TM / NT];
+      // ---------------- reverse pass on the tensor cores ----------------------------------------------------------
+      // warp w owns points 16 w .. 16 w + 15 (ONE m-tile) for both transposed GEMMs: it transforms, reads and rewrites
+      // only its own 16 columns of the activation planes / sA0, so only the weight planes need CTA barriers.
+      constexpr int LDW1 = IN1 + 8, LDW0 = W0PAD + 8;          // 152 / 56 halves: conflict-free ldmatrix rows
+      static_assert(HID * LDW1 <= PLANE, "W1 planes must fit in the weight region");
+      const int m0w = 16 * warp, g = lane >> 2, t = lane & 3;
+      __syncthreads();                                          // layer-1 planes complete, sdf dot products done
+      load_planes_generic(sWh, sWl, wp + OFF_W1, HID, IN1, IN1, LDW1);
+      // delta1[j][m] = W2[0][j] * softplus'(z1[j][m]) in place over a1 (own columns): lane -> (row j, 2 columns)
+      for (int e = lane; e < HID * 8; e += 32) {
+        const int j = e >> 3, c = m0w + 2 * (e & 7);
+        const float w = __ldg(wp + OFF_W2T + j * HID);
+        __half2 h = *reinterpret_cast<__half2*>(sAh + j * LDP + c), l = *reinterpret_cast<__half2*>(sAl + j * LDP + c);
+        const float d0 = w * dsoftplus_from_act_fast(__low2float(h) + __low2float(l));
+        const float d1 = w * dsoftplus_from_act_fast(__high2float(h) + __high2float(l));
+        __half h0, l0, h1, l1;
+        split(d0, h0, l0), split(d1, h1, l1);
+        *reinterpret_cast<__half2*>(sAh + j * LDP + c) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(sAl + j * LDP + c) = __halves2half2(l0, l1);
+      }
+      __syncthreads();                                          // W1 planes complete (and this warp's delta1 visible)
+      {
+        // g[m][i] = sum_j delta1[j][m] W1[j][i], i = 0..143 (9 pairs of n-tiles)
+        float acc1[18][4];
 #pragma unroll
-      for (int i = 0; i < HID * TM / NT; ++i) {
-        const int e = tid + i * NT, j = e >> 7, m = e & (TM - 1);
-        const float a1 = __half2float(sAh[j * LDP + m]) + __half2float(sAl[j * LDP + m]);
-        d[i] = __ldg(wp + OFF_W2T + j * HID) * dsoftplus_from_act_fast(a1);
+        for (int j = 0; j < 18; ++j) acc1[j][0] = acc1[j][1] = acc1[j][2] = acc1[j][3] = 0.f;
+        gemm_split_rows<9>(acc1, sAh, sAl, sWh, sWl, LDW1, m0w, lane);
+        __syncwarp();
+        // i < 128: delta0 = g * softplus'(z0) back into the planes (rows i, own columns) through stmatrix.trans
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = 2 * np + (q >> 1), r = q & 1;
+            const int m = m0w + 8 * r + g, nn = 8 * j + 2 * t;
+            const float v0 = acc1[j][2 * r] * dsoftplus_from_act_fast(sA0[nn * TM + m]);
+            const float v1 = acc1[j][2 * r + 1] * dsoftplus_from_act_fast(sA0[(nn + 1) * TM + m]);
+            __half h0, l0, h1, l1;
+            split(v0, h0, l0), split(v1, h1, l1);
+            hi[q] = pack_h2(h0, h1), lo[q] = pack_h2(l0, l1);
+          }
+          const int q = lane >> 3;
+          const int off = (16 * np + 8 * (q >> 1) + (lane & 7)) * LDP + m0w + 8 * (q & 1);
+          stsm4t(sAh + off, hi[0], hi[1], hi[2], hi[3]);
+          stsm4t(sAl + off, lo[0], lo[1], lo[2], lo[3]);
+        }
+        __syncwarp();   // every lane has read sA0 (layer-0 activations of the own columns): rows 48..63 may be reused
+        // i = 128..143: gradient w.r.t. the latent = g + direct path through layer 2 -> sA0 rows 48..63 (fp32)
+#pragma unroll
+        for (int j = 16; j < 18; ++j)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int m = m0w + 8 * r + g, c = 8 * (j - 16) + 2 * t;
+            sA0[(48 + c) * TM + m] = acc1[j][2 * r] + __ldg(wp + OFF_W2T + (HID + c) * HID);
+            sA0[(48 + c + 1) * TM + m] = acc1[j][2 * r + 1] + __ldg(wp + OFF_W2T + (HID + c + 1) * HID);
+          }
+      }
+      __syncthreads();                                          // every warp is done with the W1 planes
+      load_planes_generic(sWh, sWl, wp + OFF_W0, HID, W0PAD, W0PAD, LDW0);
+      __syncthreads();
+      {
+        // g_pe[m][i] = sum_n delta0[n][m] W0[n][i], i = 0..47 -> sA0 rows 0..47 (own columns)
+        float acc0[6][4];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc0[j][0] = acc0[j][1] = acc0[j][2] = acc0[j][3] = 0.f;
+        gemm_split_rows<3>(acc0, sAh, sAl, sWh, sWl, LDW0, m0w, lane);
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int m = m0w + 8 * r + g, nn = 8 * j + 2 * t;
+            sA0[nn * TM + m] = acc0[j][2 * r], sA0[(nn + 1) * TM + m] = acc0[j][2 * r + 1];
+          }
       }
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < HID * TM / NT; ++i) sAct[tid + i * NT] = d[i];
-      backward_from_delta1<true>(sAct, sW, sA0, sPts, sGp, sFlag, wp, vol, D, gi, n, o_grad);
+      backward_point_tail(sA0, sA0 + 48 * TM, sPts, sGp, sFlag, vol, D, gi, n, o_grad);
     }
     __syncthreads();  // smem is reused by the next tile
   }
