@@ -218,7 +218,6 @@ __device__ __forceinline__ void backward_from_delta1(float* sAct, float* sW, flo
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = tx * 8;
-  const int pm = tid & (TM - 1), half = tid >> 7;
   load_weights(sW, wp + OFF_W1, HID * IN1);
   __syncthreads();
   {
