@@ -796,7 +796,13 @@ int launch2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cud
 
 // tile width of the CTA-pair kernel for an N-column problem: 160 divides every UNet width (320 k), else 256 / 128
 int pick_bn2(int N) {
+  static int n256 = -1;
+  if (n256 < 0) {   // widths from which a multiple of 256 takes the 256-wide tile instead of 160 (tuning knob)
+    const char* e = getenv("O2345_BN256_MIN_N");
+    n256 = e ? atoi(e) : (1 << 30);   // r1 sweep of the UNet pass: off 4.99 ms, N >= 2560 -> 5.06, N >= 1280 -> 5.23: 160 stays
+  }
   if (N <= 64) return 0;          // single-CTA kernel with BN = 64
+  if (N % 256 == 0 && N >= n256) return 256;
   if (N % 160 == 0) return 160;
   if (N <= 128) return 128;
   return N % 256 == 0 || N > 640 ? 256 : (N % 128 == 0 ? 128 : 160);
