@@ -6,6 +6,7 @@ raises, it never routes work to PyTorch or to the CPU oracle.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -164,3 +165,20 @@ def call(name, *args):
         raise O2345Error(f"{name} failed with {rc}: {last_error()}")
     _launches += _KERNELS_PER_CALL.get(name, 1)
     return rc
+
+
+def inference_only(fn):
+    """Decorator for the module methods that run o2345 kernels: the kernels are forward / inference only, so a call with
+    autograd enabled on a module whose parameters require grad is refused with a clear error instead of silently
+    returning tensors without a graph (SURVEY.md 8(b) note 2: training stays with the reference).  Otherwise the call
+    runs under torch.no_grad()."""
+    import torch
+
+    @functools.wraps(fn)
+    def wrap(self, *args, **kwargs):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError(f"o2345 {type(self).__name__}.{fn.__name__} is inference-only: call it under torch.no_grad() or "
+                               "freeze the parameters (requires_grad_(False)); training stays with the reference")
+        with torch.no_grad():
+            return fn(self, *args, **kwargs)
+    return wrap

@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ._lib import inference_only
 from . import ops_a as A
 from .unet import _Packed
 
@@ -162,7 +163,7 @@ class AutoencoderKL(nn.Module):
         wo, bo = pk.conv(at.proj_out)
         return A.gemm(o, wo, bias=bo, residual=x)
 
-    @torch.no_grad()
+    @inference_only
     def decode(self, z):
         """z [B,4,h,w] -> image [B,3,8h,8w] fp32 (reference autoencoder.py:330-333, model.py:535-568)."""
         pk = self._pk()
@@ -186,7 +187,7 @@ class AutoencoderKL(nn.Module):
         out, _, _ = self._conv(pk, h, B, H, W, C, d.conv_out, gn=d.norm_out)
         return A.cl_to_nchw(out, B, d.conv_out.out_channels, H, W)
 
-    @torch.no_grad()
+    @inference_only
     def encode(self, x):
         """x [B,3,H,W] in [-1,1] -> Posterior over z [B,4,H/8,W/8] (reference autoencoder.py:324-328, model.py:434-459)."""
         pk = self._pk()

@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ._lib import inference_only
 from . import ops
 
 
@@ -67,10 +68,8 @@ class FeatureNet(nn.Module):
         self.smooth1 = nn.Conv2d(32, 16, 3, padding=1)
         self.smooth0 = nn.Conv2d(32, 8, 3, padding=1)
 
-    @torch.no_grad()
+    @inference_only
     def forward(self, x):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("o2345 FeatureNet is inference-only (training stays with the reference)")
         x = ops.cf32(x)
         conv0 = self.conv0(x)
         conv1 = self.conv1(conv0)

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from ._lib import inference_only
 from . import _lib as L
 from . import ops
 from .featurenet import source_maps_channel_last
@@ -63,7 +64,7 @@ class SparseNeuSRenderer(nn.Module):
         return self._u[k]
 
     # ------------------------------------------------------------------ B13 + B14
-    @torch.no_grad()
+    @inference_only
     def render(self, rays_o, rays_d, near, far, sdf_network, rendering_network, perturb_overwrite=-1,
                background_rgb=None, alpha_inter_ratio=0.0, lod=None, conditional_volume=None,
                conditional_valid_mask_volume=None, feature_maps=None, color_maps=None, w2cs=None, intrinsics=None,
@@ -168,7 +169,7 @@ class SparseNeuSRenderer(nn.Module):
                             net.sdf_layer.packed(), negate=True)
         return out["sdf"].view(resolution, resolution, resolution)
 
-    @torch.no_grad()
+    @inference_only
     def extract_geometry(self, sdf_network, bound_min, bound_max, resolution, threshold, device, occupancy_mask=None,
                          **kwargs):
         """-> (vertices float64 numpy [nv,3] in world units, triangles int numpy [nt,3], u device tensor)."""
@@ -187,7 +188,7 @@ class SparseNeuSRenderer(nn.Module):
         return vertices, tris.cpu().numpy(), u
 
     # ------------------------------------------------------------------ B11 + B12 for mesh vertices
-    @torch.no_grad()
+    @inference_only
     def blend_points(self, pts, sdf_network, rendering_network, conditional_volume, conditional_valid_mask_volume,
                      feature_maps, color_maps, w2cs, intrinsics, img_wh):
         """Vertex colours: Projector.compute_view_independent + rendering network (reference

@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ._lib import inference_only
 from . import ops
 from .featurenet import ConvBnReLU
 from .synthetic import costreg_channels
@@ -133,7 +134,7 @@ class SparseSdfNetwork(nn.Module):
         self._coords = None
 
     # ------------------------------------------------------------------ B2-B7
-    @torch.no_grad()
+    @inference_only
     def get_conditional_volume(self, feature_maps, partial_vol_origin, proj_mats, sizeH=None, sizeW=None, lod=0,
                                pre_coords=None, pre_feats=None):
         """feature_maps [1,V,C,H,W], partial_vol_origin [1,3], proj_mats [1,V,4,4] -> dict with
@@ -167,7 +168,7 @@ class SparseSdfNetwork(nn.Module):
                 "visible_mask_scale%d" % self.lod: occ, "coords_scale%d" % self.lod: self._coords}
 
     # ------------------------------------------------------------------ B8
-    @torch.no_grad()
+    @inference_only
     def sdf(self, pts, conditional_volume, lod):
         """pts [n,3] -> {'sdf_pts_scale0' [n,1], 'sdf_features_pts_scale0' [n,127], 'sampled_latent_scale0' [n,16]}."""
         out = ops.sdf_query(ops.PointSource.explicit(pts), channel_last_volume(conditional_volume),
@@ -176,7 +177,7 @@ class SparseSdfNetwork(nn.Module):
                 "sampled_latent_scale%d" % lod: out["latent"]}
 
     # ------------------------------------------------------------------ B9
-    @torch.no_grad()
+    @inference_only
     def gradient(self, x, conditional_volume, lod):
         """Analytic d sdf / d x, shape [n,1,3] (the reference differentiates with autograd, :476-499)."""
         out = ops.sdf_query(ops.PointSource.explicit(x), channel_last_volume(conditional_volume),

@@ -21,6 +21,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from ._lib import inference_only
 from . import ops_a as A
 
 _f16, _f32 = torch.float16, torch.float32
@@ -327,7 +328,7 @@ class UNetModel(nn.Module):
                 raise TypeError(type(layer))
         return x, H, W, C
 
-    @torch.no_grad()
+    @inference_only
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """Epsilon prediction.  On CUDA the ~525 kernel launches of one pass are captured once per input shape in a
         CUDA graph and replayed (the pass is launch-bound from Python: 18 ms eager vs the device time of the graph);

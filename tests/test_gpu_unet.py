@@ -24,7 +24,7 @@ def unet():
     from o2345.unet import UNetModel
     net = UNetModel()
     net.load_state_dict({k: torch.from_numpy(v) for k, v in S.unet_state(0).items()})
-    return net.cuda()
+    return net.cuda().requires_grad_(False)      # the o2345 modules are inference-only and refuse grad-enabled calls
 
 
 def test_unet_matches_reference_golden(unet, gold):

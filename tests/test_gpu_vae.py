@@ -15,7 +15,7 @@ def vae():
     from o2345.autoencoder import AutoencoderKL
     net = AutoencoderKL()
     net.load_state_dict({k: torch.from_numpy(v) for k, v in S.vae_state().items()})
-    return net.cuda()
+    return net.cuda().requires_grad_(False)
 
 
 def test_decode_and_encode_match_reference(vae):

@@ -83,3 +83,25 @@ def test_ply_writer(tmp_path):
     head, body = raw.split(b"end_header\n")
     assert b"element vertex 5" in head and b"element face 2" in head
     assert len(body) == 5 * 16 + 2 * 13
+
+
+def test_modules_refuse_autograd_calls():
+    """SURVEY.md 8(b) note 2: the kernels are inference-only; a grad-enabled call on trainable parameters must fail loudly
+    (before any kernel launch), and the same call is accepted under no_grad or with frozen parameters up to the point
+    where it needs the GPU."""
+    import pytest
+    import torch
+    from o2345.featurenet import FeatureNet
+    from o2345.unet import UNetModel
+    net = FeatureNet()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        net(torch.zeros(1, 3, 16, 16))
+    unet = UNetModel.__new__(UNetModel)          # no 859 M-parameter allocation: the guard only looks at parameters()
+    torch.nn.Module.__init__(unet)
+    unet.w = torch.nn.Parameter(torch.zeros(1))
+    with pytest.raises(RuntimeError, match="inference-only"):
+        unet.forward(torch.zeros(1, 8, 8, 8), torch.zeros(1), torch.zeros(1, 1, 768))
+    net.requires_grad_(False)
+    from o2345 import _lib
+    with pytest.raises(_lib.O2345Error):          # past the guard: now it is the missing GPU that stops the CPU call
+        net(torch.zeros(1, 3, 16, 16))

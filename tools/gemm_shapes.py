@@ -15,7 +15,7 @@ from o2345.unet import UNetModel
 from o2345.ops import _stream
 
 REPS = 10
-net = UNetModel().cuda()
+net = UNetModel().cuda().requires_grad_(False)
 net.use_cuda_graph = False
 x = torch.randn(8, 8, 32, 32, device="cuda"); t = torch.full((8,), 501, device="cuda"); ctx = torch.randn(8, 1, 768, device="cuda")
 net(x, t, ctx); torch.cuda.synchronize()

@@ -5,7 +5,7 @@ for p in (ROOT, os.path.join(ROOT, "one-2-3-45_b200")):
     sys.path.insert(0, p)
 import torch
 from o2345.unet import UNetModel
-net = UNetModel().cuda()           # default torch init is fine for timing
+net = UNetModel().cuda().requires_grad_(False)           # default torch init is fine for timing
 net.use_cuda_graph = False
 x = torch.randn(8, 8, 32, 32, device="cuda"); t = torch.full((8,), 501, device="cuda"); ctx = torch.randn(8, 1, 768, device="cuda")
 net(x, t, ctx); torch.cuda.synchronize()
