@@ -1,0 +1,45 @@
+"""GPU: the two command-line entry points (mirrors of the reference's run.py and exp_runner_generic_blender_val.py)
+end to end through the files they exchange."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "one-2-3-45_b200")
+
+
+def test_run_py_then_exp_runner(tmp_path, monkeypatch):
+    from PIL import Image
+    sys.path.insert(0, PKG)
+    import exp_runner_generic_blender_val as runner
+    import run as run_cli
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(3)
+    rgba = np.zeros((300, 280, 4), np.uint8)
+    rgba[60:240, 50:230, :3] = rng.integers(0, 255, (180, 180, 3), dtype=np.uint8)
+    rgba[60:240, 50:230, 3] = 255                                  # an "object" on a transparent background
+    png = str(tmp_path / "thing.png")
+    Image.fromarray(rgba, "RGBA").save(png)
+
+    ply = run_cli.main(["--img_path", png, "--half_precision", "--mesh_resolution", "64"])
+    exp_dir = tmp_path / "exp" / "thing"
+    assert os.path.samefile(ply, exp_dir / "mesh.ply")
+    assert len(os.listdir(exp_dir / "stage1_8")) == 8 and len(os.listdir(exp_dir / "stage2_8")) == 32
+    assert (exp_dir / "pose.json").exists()
+    first = (exp_dir / "mesh.ply").read_bytes()
+    assert first.startswith(b"ply") and len(first) > 1000
+
+    # the reconstruction runner on the folder run.py wrote: the PNGs are lossless, so the mesh is the same mesh
+    mesh = runner.main(["--specific_dataset_name", str(exp_dir), "--mode", "export_mesh", "--resolution", "64",
+                        "--conf", "confs/one2345_lod0_val_demo.conf"])
+    assert (exp_dir / "mesh.ply").read_bytes() == first
+    assert mesh["vertices"].shape[1] == 3 and mesh["triangles"].max() < len(mesh["vertices"])
+
+    out = runner.main(["--specific_dataset_name", str(exp_dir), "--mode", "val"])
+    assert out["color"].shape == (256 * 256, 3) and np.isfinite(out["color"]).all() and np.isfinite(out["depth"]).all()
+    assert (exp_dir / "val_color.png").exists()
+    with pytest.raises(SystemExit):
+        runner.main(["--specific_dataset_name", str(exp_dir), "--mode", "train"])
