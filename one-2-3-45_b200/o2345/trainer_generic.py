@@ -147,7 +147,7 @@ class GenericTrainer(nn.Module):
             tm = trans_mat.cpu().numpy().reshape(-1, 4, 4)[0]
             vh = np.concatenate([vertices, np.ones_like(vertices[:, :1])], axis=1)
             vertices = (vh @ tm.T)[:, :3]
-        colors = np.array(rgb.cpu() * 255, dtype=np.uint8)
+        colors = (rgb.cpu() * 255).numpy().astype(np.uint8)
         if self.base_exp_dir is not None:
             os.makedirs(self.base_exp_dir, exist_ok=True)
             write_ply(os.path.join(self.base_exp_dir, 'mesh.ply'), vertices, triangles, colors)
