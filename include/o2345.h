@@ -274,7 +274,7 @@ typedef struct {
                             activation (the ResBlock's per-image emb_layers output, openaimodel.py:266-273) */
   int64_t rowbias_ld;
   int rows_per_group;
-  int act;               /* 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU (attention.py:37-44): the N columns come in chunks of
+  int act;               /* 0 none, 1 SiLU, 2 GELU(erf), 4 QuickGELU x*sigmoid(1.702x) (CLIP), 3 GEGLU (attention.py:37-44): the N columns come in chunks of
                             32 = 16 values followed by their 16 gates, C gets N/2 columns value * gelu(gate) */
   float alpha;           /* scale on the accumulator */
   int out_f32;           /* C is fp32 instead of fp16 */
@@ -322,7 +322,7 @@ int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float
 int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream);
 /* Fused multi-head self-attention (ldm/modules/attention.py:170-193): out[b, n, h*d + j] = softmax(q k^T * scale) v.
  * q, k, v: fp16 [B*N, >= H*d] views with a common row stride ld (e.g. column blocks of a fused qkv projection);
- * d in {40, 80, 160}; scores stay on chip (mma.sync m16n8k16, fp32 online softmax). */
+ * d in {40, 64, 80, 160} (64: CLIP ViT-L/14); scores stay on chip (mma.sync m16n8k16, fp32 online softmax). */
 int o2345_attention_f16(const void* q, const void* k, const void* v, int B, int N, int H, int d, int ld, void* out,
                         int ldo, float scale, o2345_stream_t stream);
 /* y[M,I] = x[:, :I] * gelu(x[:, I:2I]) */
@@ -339,6 +339,17 @@ int o2345_cl_f16_to_nchw_f32(const void* x, int B, int C, int HW, int ldx, float
 int o2345_cfg_ddim_update(const float* x, const float* eps, const float* noise, int64_t n, float scale, float a_t,
                           float a_prev, float sigma_t, float sqrt_one_minus_at, float* x_prev, float* pred_x0,
                           o2345_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row A8: front end of the CLIP ViT-L/14 image tower (FrozenCLIPImageEmbedder.preprocess + the patch embedding's patch
+ * gather, ldm/modules/encoders/modules.py:362-370).  mean3 / std3 are HOST pointers to three floats.
+ * out [B * (res/patch)^2, kp] fp16: row (b, py, px), column (c, ky, kx) = bicubic(align_corners) resize of x [B,3,H,W]
+ * (fp32, [-1,1]) to res x res, mapped to [0,1] and normalised; columns 3 patch^2 .. kp-1 zero.
+ * ------------------------------------------------------------------------------------------ */
+int o2345_clip_patches(const float* x, int B, int H, int W, int res, int patch, const float* mean3, const float* std3, int kp,
+                       void* out, o2345_stream_t stream);
+/* tok [B*N, d] fp16: row 0 of every image := class_embedding + pos[0]; rows n >= 1 += pos[n] (cls, pos fp32 on the device) */
+int o2345_clip_add_positions(void* tok, const float* cls, const float* pos, int B, int N, int d, o2345_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -155,7 +155,7 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
                                    int ldo, float scale, o2345_stream_t stream) {
   O2345_CHECK_ARG(q && k && v && out, "null pointer");
   O2345_CHECK_ARG(B > 0 && N > 0 && H > 0 && (ld % 8) == 0 && (ldo % 2) == 0, "bad sizes");
-  O2345_CHECK_ARG(d == 40 || d == 80 || d == 160, "head dim must be 40, 80 or 160");
+  O2345_CHECK_ARG(d == 40 || d == 64 || d == 80 || d == 160, "head dim must be 40, 64, 80 or 160");
   O2345_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0, "q/k/v must be 16-byte aligned");
   dim3 grid(cdiv(N, QT), B * H);
   float sl2 = scale * 1.4426950408889634f;
@@ -168,9 +168,10 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
     attr = true;
   }
   if (d == 40) O2345_CUDA(launch_pdl(attention_kernel<40, 48>, dim3(grid), dim3(128), (size_t)(smem(48)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
+  else if (d == 64) O2345_CUDA(launch_pdl(attention_kernel<64, 64>, dim3(grid), dim3(128), (size_t)(smem(64)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
   else if (d == 80) O2345_CUDA(launch_pdl(attention_kernel<80, 80>, dim3(grid), dim3(128), (size_t)(smem(80)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
   else if (d == 160) O2345_CUDA(launch_pdl(attention_kernel<160, 160>, dim3(grid), dim3(128), (size_t)(smem(160)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
-  else { set_error("o2345_attention_f16: head dim %d not built (40 / 80 / 160)", d); return O2345_EUNSUPPORTED; }
+  else { set_error("o2345_attention_f16: head dim %d not built (40 / 64 / 80 / 160)", d); return O2345_EUNSUPPORTED; }
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

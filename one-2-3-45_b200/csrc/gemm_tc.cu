@@ -153,7 +153,7 @@ struct GemmParams {
   const __half* residual;      // [M, ldc] or nullptr, added after the activation
   void* C;
   int out_f32;                 // 0: fp16 output, 1: fp32 output
-  int act;                     // 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU: columns come in chunks of 32 = 16 values + their 16 gates,
+  int act;                     // 0 none, 1 SiLU, 2 GELU(erf), 4 QuickGELU x sigmoid(1.702 x), 3 GEGLU: columns come in chunks of 32 = 16 values + their 16 gates,
                                //    out[:, 16 j + e] = v_e * gelu(g_e); C has N / 2 columns
   float alpha;                 // scale applied to the accumulator before bias
   int batched;                 // 4-D tensor maps (K, rows, h, b)
@@ -177,6 +177,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == 1) return x / (1.f + __expf(-x));
   if (act == 2) return gelu_erf(x);
+  if (act == 4) return x / (1.f + __expf(-1.702f * x));   // QuickGELU (CLIP)
   return x;
 }
 
@@ -297,6 +298,7 @@ template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
   if (ACT == 1) return __fdividef(x, 1.f + __expf(-x));
   if (ACT == 2) return gelu_erf(x);
+  if (ACT == 4) return __fdividef(x, 1.f + __expf(-1.702f * x));
   return x;
 }
 
@@ -374,6 +376,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, uint32_t tm
     case 1: stage_rows<BN, 1>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
     case 2: stage_rows<BN, 2>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
     case 3: stage_rows<BN, 3>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
+    case 4: stage_rows<BN, 4>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
     default: stage_rows<BN, 0>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
   }
   __syncwarp();
@@ -814,7 +817,7 @@ int fill_epilogue(GemmParams& p, const o2345_epilogue* ep, int M, int N, int64_t
   p.bias = nullptr, p.rowbias = nullptr, p.rowbias_ld = 0, p.rows_per_group = 1, p.residual = nullptr;
   p.out_f32 = 0, p.act = 0, p.alpha = 1.f, p.trace = g_trace;
   if (!ep) return O2345_OK;
-  O2345_CHECK_ARG(ep->act >= 0 && ep->act <= 3, "unknown activation");
+  O2345_CHECK_ARG(ep->act >= 0 && ep->act <= 4, "unknown activation");
   O2345_CHECK_ARG(!ep->rowbias || (ep->rows_per_group > 0 && (ep->rowbias_ld % 8) == 0 && ((uintptr_t)ep->rowbias % 16) == 0),
                   "row bias: rows_per_group > 0, 16-byte aligned, row stride a multiple of 8");
   O2345_CHECK_ARG(ep->act != 3 || ((N % 32) == 0 && (ldc % 8) == 0 && !ep->residual && !ep->rowbias),

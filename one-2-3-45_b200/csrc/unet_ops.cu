@@ -13,6 +13,8 @@
 //   timestep_embedding   util.py:151-171
 //   cfg_ddim_update      ddim.py:212-243 (classifier-free guidance + x0 / direction / noise update)
 //   layout converters    NCHW fp32 <-> channel-last fp16, channel concat
+//   clip_patches / clip_add_positions   CLIP image tower front end (encoders/modules.py:362-370): bicubic resize +
+//                        normalisation + patch gather in one pass, class token and positional embeddings
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -294,6 +296,63 @@ __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float*
   if (pred_x0) pred_x0[i] = p0;
 }
 
+// ---- CLIP image tower front end (reference ldm/modules/encoders/modules.py:362-370 + the patch embedding's im2col)
+// bicubic weights of torch's upsample_bicubic2d (A = -0.75) for the taps at offsets -1, 0, 1, 2
+__device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  float x = t + 1.f;
+  w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+  w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  x = 1.f - t;
+  w[2] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  x = 2.f - t;
+  w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+// x [B,3,H,W] fp32 in [-1,1] -> rows (b, py, px) x columns (c, ky, kx) of the res x res bicubic resize (align_corners),
+// mapped to [0,1] and normalised with the CLIP mean / std; fp16; columns 3 P^2 .. kp-1 are zero padding
+__global__ void clip_patches_kernel(const float* __restrict__ x, int B, int H, int W, int res, int P, float m0, float m1, float m2,
+                                    float s0, float s1, float s2, int kp, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int g = res / P, kk = 3 * P * P;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * g * g * kp) return;
+  const int col = (int)(i % kp);
+  const int64_t row = i / kp;
+  if (col >= kk) { out[i] = __float2half(0.f); return; }
+  const int c = col / (P * P), ky = (col / P) % P, kx = col % P;
+  const int px = (int)(row % g), py = (int)((row / g) % g), b = (int)(row / (g * g));
+  const int oy = py * P + ky, ox = px * P + kx;
+  const float sy = (float)oy * (float)(H - 1) / (float)(res - 1), sx = (float)ox * (float)(W - 1) / (float)(res - 1);
+  const float fy = floorf(sy), fx = floorf(sx);
+  float wy[4], wx[4];
+  cubic_w(sy - fy, wy), cubic_w(sx - fx, wx);
+  const float* src = x + ((int64_t)b * 3 + c) * H * W;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int yy = min(max((int)fy - 1 + j, 0), H - 1);
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r = fmaf(__ldg(src + (int64_t)yy * W + min(max((int)fx - 1 + k, 0), W - 1)), wx[k], r);
+    acc = fmaf(r, wy[j], acc);
+  }
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  out[i] = __float2half_rn(((acc + 1.f) * 0.5f - mean) / sd);
+}
+
+// tok [B*N, d] fp16: row n = 0 of every image becomes class_embedding + pos[0]; rows n >= 1 (patch embeddings) += pos[n]
+__global__ void clip_add_positions_kernel(__half* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos, int B,
+                                          int N, int d) {
+  pdl_wait();
+  pdl_trigger();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * N * d) return;
+  const int c = (int)(i % d), n = (int)((i / d) % N);
+  const float v = n == 0 ? cls[c] : __half2float(tok[i]);
+  tok[i] = __float2half_rn(v + pos[(int64_t)n * d + c]);
+}
+
 }  // namespace
 }  // namespace o2345
 
@@ -411,6 +470,27 @@ extern "C" int o2345_cfg_ddim_update(const float* x, const float* eps, const flo
                                      o2345_stream_t stream) {
   O2345_CHECK_ARG(x && eps && x_prev, "null pointer");
   O2345_CUDA(launch_pdl(cfg_ddim_update_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), ST, x, eps, noise, n, scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, x_prev, pred_x0));
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_clip_patches(const float* x, int B, int H, int W, int res, int patch, const float* mean3, const float* std3, int kp,
+                                  void* out, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && mean3 && std3 && out, "null pointer");
+  O2345_CHECK_ARG(B > 0 && H > 1 && W > 1 && res > 1 && patch > 0 && res % patch == 0 && kp >= 3 * patch * patch && (kp % 8) == 0,
+                  "bad sizes (res must be a multiple of patch, kp a multiple of 8 >= 3 patch^2)");
+  const int g = res / patch;
+  const int64_t total = (int64_t)B * g * g * kp;
+  O2345_CUDA(launch_pdl(clip_patches_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)0, ST, x, B, H, W, res, patch, mean3[0], mean3[1],
+                        mean3[2], std3[0], std3[1], std3[2], kp, (__half*)out));
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_clip_add_positions(void* tok, const float* cls, const float* pos, int B, int N, int d, o2345_stream_t stream) {
+  O2345_CHECK_ARG(tok && cls && pos && B > 0 && N > 0 && d > 0, "bad arguments");
+  O2345_CUDA(launch_pdl(clip_add_positions_kernel, dim3(cdiv((int64_t)B * N * d, 256)), dim3(256), (size_t)0, ST, (__half*)tok, cls, pos,
+                        B, N, d));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

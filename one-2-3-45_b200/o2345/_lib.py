@@ -103,6 +103,9 @@ _SIGS = {
     "o2345_cl_f16_to_nchw_f32": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "o2345_cfg_ddim_update": (C.c_int, [c_fp, c_fp, c_fp, c_i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                         c_fp, c_fp, c_fp]),
+    "o2345_clip_patches": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                     C.c_int, c_fp, c_fp]),
+    "o2345_clip_add_positions": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_fp]),
     "o2345_ray_composite": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float,
                                       C.c_float, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
 }

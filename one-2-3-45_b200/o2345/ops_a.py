@@ -38,7 +38,7 @@ def _epilogue(bias=None, residual=None, rowbias=None, rows_per_group=1, act=0, a
                       act=int(act), alpha=float(alpha), out_f32=int(out_f32))
 
 
-ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU, ACT_QUICKGELU = 0, 1, 2, 3, 4
 
 
 def gemm(a, b, bias=None, residual=None, act=0, alpha=1.0, out_dtype=_f16, out=None, rowbias=None, rows_per_group=1):
@@ -204,3 +204,20 @@ def conv3x3(x, B, H, W, C, weight, bias=None, residual=None, act=0, out_dtype=_f
 
 def conv3x3_supported(W, C):
     return C % 8 == 0 and C >= 64 and (128 % W == 0 or W % 128 == 0)
+
+
+def clip_patches(x, res, patch, mean, std, kp):
+    """[-1,1] images [B,3,H,W] -> fp16 [B*(res/patch)^2, kp]: bicubic resize + CLIP normalisation + patch gather."""
+    B, _, H, W = x.shape
+    x = x.to(_f32).contiguous()
+    g = res // patch
+    out = torch.empty(B * g * g, kp, dtype=_f16, device=x.device)
+    m3 = (C.c_float * 3)(*[float(v) for v in mean])       # host constants (no device read-back)
+    s3 = (C.c_float * 3)(*[float(v) for v in std])
+    L.call("o2345_clip_patches", _v(x), B, H, W, int(res), int(patch), m3, s3, int(kp), _v(out), _stream())
+    return out
+
+
+def clip_add_positions(tok, cls, pos, B, N, d):
+    L.call("o2345_clip_add_positions", _v(tok), _p(cls, _f32), _p(pos, _f32), B, N, d, _stream())
+    return tok

@@ -343,3 +343,27 @@ def vae_state(seed=10, gain=0.7):
         else:
             sd[k] = 0.02 * rng.standard_normal(shp, dtype=np.float32)
     return sd
+
+
+def clip_state(seed=20, gain=0.7):
+    """State dict of FrozenCLIPImageEmbedder (OpenAI CLIP ViT-L/14 vision tower, 304 M parameters, keys
+    `model.visual.*`), same recipe as unet_state; embeddings N(0, 0.02) like CLIP's own initialisation scale."""
+    import torch
+    from .clip_image import FrozenCLIPImageEmbedder
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in FrozenCLIPImageEmbedder().state_dict().items()}
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        if k.endswith(("class_embedding", "positional_embedding")):
+            sd[k] = 0.02 * rng.standard_normal(shp, dtype=np.float32)
+        elif k.endswith("visual.proj"):
+            sd[k] = rng.standard_normal(shp, dtype=np.float32) * np.float32(gain / math.sqrt(shp[0]))
+        elif len(shp) >= 2:
+            sd[k] = rng.standard_normal(shp, dtype=np.float32) * np.float32(gain / math.sqrt(int(np.prod(shp[1:]))))
+        elif ".ln_" in k:
+            sd[k] = (1.0 + 0.1 * rng.standard_normal(shp, dtype=np.float32)) if k.endswith("weight") else \
+                (0.05 * rng.standard_normal(shp, dtype=np.float32))
+        else:
+            sd[k] = 0.02 * rng.standard_normal(shp, dtype=np.float32)
+    return sd

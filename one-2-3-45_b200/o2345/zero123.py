@@ -6,9 +6,10 @@ Mirrors, with the same call signatures:
     763-860,888-984,1441-1474) -- the `hybrid` conditioning of configs/sd-objaverse-finetune-c_concat-256.yaml;
   * sample_model_batch, predict_stage1_gradio, zero123_infer            (reference utils/zero123_utils.py:60-178);
   * stage1_run / stage2_run view bookkeeping                             (reference run.py:18-54).
-Out of scope here: the CLIP image tower (row A8) -- `cond_stage_model` is a pluggable
-callable, by default a seeded stand-in embedding -- and the LoFTR elevation search (the polar angle is an input).
-Checkpoint keys: `model.diffusion_model.*`, `first_stage_model.*`, `cc_projection.*` load directly.
+The CLIP image tower (row A8) lives in o2345/clip_image.py (`FrozenCLIPImageEmbedder`); `cond_stage_model` is pluggable and
+build_zero123(clip=True) attaches it (default: a seeded stand-in embedding, which is what bench.py times in round 1).
+Out of scope here: the LoFTR elevation search (the polar angle is an input).
+Checkpoint keys: `model.diffusion_model.*`, `first_stage_model.*`, `cc_projection.*`, `cond_stage_model.*` load directly.
 """
 from __future__ import annotations
 
@@ -84,9 +85,10 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def get_learned_conditioning(self, c):
         if self.cond_stage_model is None:
-            g = torch.Generator().manual_seed(7)            # stand-in for FrozenCLIPImageEmbedder (row A8, not built)
+            g = torch.Generator().manual_seed(7)            # no conditioning encoder attached: a fixed embedding
             return torch.randn(c.shape[0], 1, 768, generator=g).to(c.device)
-        return self.cond_stage_model(c)
+        enc = getattr(self.cond_stage_model, "encode", None)   # reference ddpm.py:619-626
+        return enc(c) if callable(enc) else self.cond_stage_model(c)
 
     @torch.no_grad()
     def project_condition(self, c):
@@ -183,9 +185,14 @@ def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=
     return stage1, stage2, pose
 
 
-def build_zero123(device, seed=0):
-    """LatentDiffusion with seeded random weights (no checkpoint exists offline)."""
+def build_zero123(device, seed=0, clip=False):
+    """LatentDiffusion with seeded random weights (no checkpoint exists offline).  clip=True attaches the CLIP ViT-L/14
+    image tower (row A8, o2345/clip_image.py) as cond_stage_model instead of the fixed stand-in embedding."""
     m = LatentDiffusion()
+    if clip:
+        from .clip_image import FrozenCLIPImageEmbedder
+        m.cond_stage_model = FrozenCLIPImageEmbedder()
+        m.cond_stage_model.load_state_dict({k: torch.from_numpy(v) for k, v in S.clip_state(seed + 20).items()})
     m.model.diffusion_model.load_state_dict({k: torch.from_numpy(v) for k, v in S.unet_state(seed).items()})
     m.first_stage_model.load_state_dict({k: torch.from_numpy(v) for k, v in S.vae_state(seed + 10).items()})
     for p in m.parameters():
