@@ -4,10 +4,11 @@
 
 Headline metric (BASELINE.json, configs[1]): "sec/mesh end-to-end (256x256 in)".  One step = one 256x256 input
 image -> Zero123 stage 1 + stage 2 (10 DDIM sampler calls = 2x76 + 8x49 = 544 UNet iterations at the CFG batch
-of 8, fp16 tensor-core GEMMs with fp32 accumulate; 10 VAE encodes, 40 VAE decodes) -> 32 views -> FeatureNet ->
+of 8, fp16 tensor-core GEMMs with fp32 accumulate; 10 CLIP ViT-L/14 image embeddings, 10 VAE encodes, 40 VAE decodes)
+-> 32 views -> FeatureNet ->
 96^3 cost volume -> sparse U-Net -> 256^3 SDF grid -> marching cubes -> vertex colours -> mesh arrays on the host
 (`o2345.pipeline.image_to_mesh`).  Not inside the step (out of scope): SAM / rembg
-preprocessing, the CLIP image tower (a fixed embedding stands in) and the LoFTR elevation search (polar angle 60).
+preprocessing and the LoFTR elevation search (polar angle 60).
 `value` is timed on the device with CUDA events; `e2e` is the wall clock of the same public call starting from a
 pinned host image and ending with the mesh on the host (the pipeline itself moves the generated views through the
 host as uint8, as the reference's PNG hand-off does).  The second BASELINE metric, "volume-render M rays/sec", is
@@ -43,7 +44,7 @@ CONFIG = {"workload": "configs[1]: single 256x256 image -> mesh: Zero123 75/50-s
                       "+ 96^3 cost volume + 256^3 SDF grid + marching cubes, 1 image per GPU",
           "views": N_VIEWS, "vol_dim": VOL, "mesh_resolution": MESH_RES, "ddim_steps": [75, 50], "cfg_scale": 3.0,
           "l2": "inputs larger than L2 (1.72 GB fp16 UNet weights stream every iteration; 470 MB feature maps)",
-          "not_in_step": "SAM/rembg, CLIP image tower (fixed embedding), LoFTR elevation search (polar angle 60)",
+          "not_in_step": "SAM/rembg, LoFTR elevation search (polar angle 60)",
           "parallelism": "one image per GPU"}
 # algorithmic work, SURVEY.md section 8(d)
 UNET_FLOP_PER_SAMPLE = 176.3e9
@@ -124,7 +125,7 @@ def run_gpu(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     tr = build_networks(dev, vol_dim=VOL, states=S.all_states(0), perturb=0.0)
-    z123 = build_zero123(dev, seed=0).half()            # `--half_precision`: fp16-rounded schedule buffers
+    z123 = build_zero123(dev, seed=0, clip=True).half()   # `--half_precision`: fp16-rounded schedule buffers; CLIP tower attached
     # the only collective on the path: weights from rank 0 over NVLink (no-op at N = 1)
     sharding.broadcast_module_weights([tr.pyramid_feature_network_geometry_lod0, tr.sdf_network_lod0,
                                        tr.rendering_network_lod0, tr.variance_network_lod0, z123], src=0)
@@ -300,7 +301,7 @@ def render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk):
     drift = float((f_bl()[0] - rgb32).abs().max())
     t_roof = max(RAY_FLOP / (pk["bf16_tflops"] * 1e12), RAY_GATHER_BYTES / (pk["hbm_gbs"] * 1e9)) * N_RAYS
     return {"metric": "volume-render M rays/sec", "value": N_RAYS / (ms_img * 1e-3) / 1e6, "unit": "M rays/s",
-            "workload": "65536 rays x (64+64) samples x 32 views, volume + feature maps resident; SDF MLP fp32, view-blending "
+            "workload": "65536 rays x (64+64) samples x 32 views, volume + feature maps resident; SDF MLP split-fp16 tensor cores (fp32-grade), view-blending "
                         "MLPs on tensor cores (fp16 operands, fp32 accumulate / statistics)",
             "image_ms": ms_img, "frac_of_survey_contract": t_roof * 1e3 / ms_img,
             "kernels_first_chunk": {
@@ -341,6 +342,11 @@ def cpu_reference():
         w0 = time.perf_counter()
         VO.encode_moments(sd_v, torch.rand(1, 3, 256, 256, generator=g) * 2 - 1)
         t_enc = time.perf_counter() - w0
+        from oracle import clip_oracle as CO
+        sd_c = {k: torch.from_numpy(v) for k, v in S.clip_state(20).items()}
+        w0 = time.perf_counter()
+        CO.embed(sd_c, torch.rand(1, 3, 256, 256, generator=g) * 2 - 1)
+        t_clip = time.perf_counter() - w0
         st = states_torch(0)
         cams = S.scene_cameras(S.pose_json(60.0), n_src=N_VIEWS, img_wh=(W, H))
         imgs = torch.from_numpy(S.images(N_VIEWS + 1, H, W, seed=1234))[1:]
@@ -352,10 +358,10 @@ def cpu_reference():
         w0 = time.perf_counter()
         O.sdf_grid(cv["dense"], st["sdf_network_lod0"], 48)
         t_grid = (time.perf_counter() - w0) * (MESH_RES / 48.0) ** 3
-    total = UNET_ITERS * t_unet + 40 * t_dec + 10 * t_enc + t_vol + t_grid
+    total = UNET_ITERS * t_unet + 40 * t_dec + 10 * t_enc + 10 * t_clip + t_vol + t_grid
     return {"value": total, "unit": "s/mesh", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"1 UNet iteration at batch 8 ({t_unet:.2f} s, x{UNET_ITERS}) + 1 VAE decode ({t_dec:.2f} s, x40) + 1 VAE encode "
-                      f"({t_enc:.2f} s, x10) + full 96^3 volume build ({t_vol:.1f} s) + 48^3 SDF grid scaled to 256^3 ({t_grid:.0f} s); "
+                      f"({t_enc:.2f} s, x10) + 1 CLIP image embedding ({t_clip:.2f} s, x10) + full 96^3 volume build ({t_vol:.1f} s) + 48^3 SDF grid scaled to 256^3 ({t_grid:.0f} s); "
                       f"marching cubes / vertex colours not included; weights generated in {t_setup:.0f} s (untimed)"}
 
 
