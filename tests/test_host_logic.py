@@ -105,3 +105,40 @@ def test_modules_refuse_autograd_calls():
     from o2345 import _lib
     with pytest.raises(_lib.O2345Error):          # past the guard: now it is the missing GPU that stops the CPU call
         net(torch.zeros(1, 3, 16, 16))
+
+
+def test_geglu_pack_matches_the_epilogue_contract():
+    """ops_a.geglu_pack reorders the GEGLU projection so that every 32-column chunk holds 16 values followed by their 16
+    gates (what the ACT_GEGLU GEMM epilogue consumes); emulated here in torch."""
+    import torch
+    from o2345 import ops_a
+    g = torch.Generator().manual_seed(0)
+    I, K, M = 64, 40, 9
+    w, b = torch.randn(2 * I, K, generator=g), torch.randn(2 * I, generator=g)
+    x = torch.randn(M, K, generator=g)
+    wp, bp = ops_a.geglu_pack(w, b)
+    y = (x @ wp.t() + bp).view(M, -1, 2, 16)                     # [M, chunk, {value, gate}, 16]
+    got = (y[:, :, 0] * torch.nn.functional.gelu(y[:, :, 1])).reshape(M, I)
+    full = x @ w.t() + b
+    want = full[:, :I] * torch.nn.functional.gelu(full[:, I:])
+    assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_command_lines_parse_the_reference_arguments():
+    import os
+    import sys
+    import pytest
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "one-2-3-45_b200")
+    sys.path.insert(0, pkg)
+    import exp_runner_generic_blender_val as runner
+    import run as run_cli
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("argument handling without a GPU is what this checks")
+    with pytest.raises(SystemExit, match="CUDA"):                 # parses the reference's flags, then refuses to run on the CPU
+        run_cli.main(["--img_path", "x.png", "--gpu_idx", "0", "--half_precision", "--mesh_resolution", "128", "--output_format", ".ply"])
+    with pytest.raises(SystemExit, match="CUDA"):
+        runner.main(["--specific_dataset_name", "/tmp/x", "--mode", "export_mesh", "--conf", "confs/one2345_lod0_val_demo.conf",
+                     "--resolution", "256"])
+    with pytest.raises(SystemExit, match="only 'export_mesh' and 'val'"):
+        runner.main(["--mode", "train"])
