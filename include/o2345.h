@@ -32,7 +32,7 @@ extern "C" {
 #define O2345_ECUDA (-2)
 #define O2345_EUNSUPPORTED (-3)
 
-#define O2345_ABI_VERSION 1
+#define O2345_ABI_VERSION 2   /* 2: o2345_epilogue, precision arguments of sdf_query / render_blend, GroupNorm as affine */
 
 typedef void* o2345_stream_t;
 

@@ -111,6 +111,7 @@ _SIGS = {
 }
 
 EXPORTED = tuple(_SIGS)
+ABI_VERSION = 2          # include/o2345.h: O2345_ABI_VERSION
 _lib = None
 
 
@@ -129,6 +130,9 @@ def load():
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
+        if lib.o2345_abi_version() != ABI_VERSION:
+            raise O2345Error(f"{LIB_PATH} has ABI version {lib.o2345_abi_version()}, this binding expects {ABI_VERSION}: "
+                             "rebuild with `python one-2-3-45_b200/build.py`")
         _lib = lib
     return _lib
 
