@@ -162,10 +162,9 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
   cudaStream_t st = (cudaStream_t)stream;
   const __half *qh = (const __half*)q, *kh = (const __half*)k, *vh = (const __half*)v;
   auto smem = [](int dp) { return (size_t)((QT + 2 * KT) * (dp + 8)) * sizeof(__half); };
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(160)));
-    attr = true;
   }
   if (d == 40) O2345_CUDA(launch_pdl(attention_kernel<40, 48>, dim3(grid), dim3(128), (size_t)(smem(48)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
   else if (d == 64) O2345_CUDA(launch_pdl(attention_kernel<64, 64>, dim3(grid), dim3(128), (size_t)(smem(64)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));

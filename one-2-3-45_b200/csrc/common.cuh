@@ -32,6 +32,19 @@ void set_error(const char* fmt, ...);
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// "Once per device" guard for per-function attributes (cudaFuncSetAttribute applies to the CURRENT device only, and a
+// process may drive several devices, e.g. run.py --gpu_idx): need() is true the first time it is called on a device.
+struct PerDeviceOnce {
+  unsigned long long seen = 0;
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d > 63) return true;
+    if ((seen >> d) & 1ull) return false;
+    seen |= 1ull << d;
+    return true;
+  }
+};
+
 // Number of SMs of the current device (cached).  Grids of persistent kernels are sized
 // as a multiple of this (148 on B200).
 int sm_count();

@@ -772,10 +772,9 @@ int finalize(const GemmParams& p, cudaStream_t st) {
 template <int BN, int STAGES>
 int launch1(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
   constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + epi_smem_bytes(BN) + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     O2345_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
   }
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), batch > 0 ? batch : (p.splits > 1 ? p.splits : 1));
   O2345_CUDA(launch_pdl(gemm_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), (size_t)(SMEM), st, a, b, p));
@@ -786,10 +785,9 @@ int launch1(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int
 template <int BN, int STAGES>
 int launch2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
   constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 1) * 8 + 16 + epi_smem_bytes(BN) + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     O2345_CUDA(cudaFuncSetAttribute(gemm2_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr = true;
   }
   dim3 grid(2 * cdiv(p.M, 2 * BM), cdiv(p.N, BN), p.splits > 1 ? p.splits : 1);
   O2345_CUDA(launch_pdl(gemm2_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), (size_t)(SMEM), st, a, b, p));

@@ -587,10 +587,9 @@ extern "C" int o2345_ray_upsample(const float* rays_o, const float* rays_d, int6
   O2345_CHECK_ARG(S >= 2 && S <= 512 && n_new >= 1, "bad sample counts");
   if (R == 0) return O2345_OK;
   size_t smem = (size_t)S * UPT * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     O2345_CUDA(cudaFuncSetAttribute(ray_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * UPT * 4));
-    attr_done = true;
   }
   ray_upsample_kernel<<<cdiv(R, UPT), UPT, smem, (cudaStream_t)stream>>>(rays_o, rays_d, R, z, sdf, S, inv_s, occ, D, u, n_new, new_z);
   O2345_LAUNCH_CHECK();
@@ -635,10 +634,9 @@ extern "C" int o2345_render_blend(const o2345_points* src, int64_t n, const uint
   if (precision == O2345_BLEND_TC_FP16)
     return launch_render_blend_tc(src, n, active, vol_cl, occ, D, views, dir_mode, query_center, dirs, rnet_pack, rgb, nvalid,
                                   (cudaStream_t)stream);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     O2345_CUDA(cudaFuncSetAttribute(render_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLEND_SMEM));
-    attr_done = true;
   }
   int64_t need = (n + BW - 1) / BW;
   int grid = (int)(need < (int64_t)sm_count() ? need : (int64_t)sm_count());

@@ -542,10 +542,9 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
 int launch_render_blend_tc(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl, const float* occ, int D,
                            const o2345_views* views, int dir_mode, const float* query_center, const float* dirs,
                            const float* rnet_pack, float* rgb, int32_t* nvalid, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     O2345_CUDA(cudaFuncSetAttribute(render_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr_done = true;
   }
   int64_t need = (n + TW - 1) / TW;
   int64_t cap = 2 * (int64_t)sm_count();

@@ -254,11 +254,10 @@ extern "C" int o2345_sdf_query(const o2345_points* src, int64_t n, const float* 
   if (precision == O2345_SDF_TC_SPLIT)
     return launch_sdf_query_tc(src, n, vol_cl, D, wpack, active, inactive_sdf, negate ? -1.f : 1.f, sdf, feat, latent, grad,
                                (cudaStream_t)stream);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     O2345_CUDA(cudaFuncSetAttribute(sdf_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
     O2345_CUDA(cudaFuncSetAttribute(sdf_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_GRAD));
-    attr_done = true;
   }
   int64_t ntiles = (n + TM - 1) / TM;
   int grid = (int)(ntiles < (int64_t)sm_count() ? ntiles : (int64_t)sm_count());

@@ -420,11 +420,10 @@ sdf_query_tc_kernel(o2345_points src, int64_t n, const float* __restrict__ vol, 
 
 int launch_sdf_query_tc(const o2345_points* src, int64_t n, const float* vol_cl, int D, const float* wpack, const uint8_t* active,
                         float inactive_sdf, float sign, float* sdf, float* feat, float* latent, float* grad, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     O2345_CUDA(cudaFuncSetAttribute(sdf_query_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC_FWD));
     O2345_CUDA(cudaFuncSetAttribute(sdf_query_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC_GRAD));
-    attr_done = true;
   }
   int64_t tiles = (n + TM - 1) / TM;
   int grid = (int)(tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count());
