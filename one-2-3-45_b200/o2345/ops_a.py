@@ -1,4 +1,9 @@
-"""Path A (Zero123 DDIM / UNet / VAE) tensor-level wrappers over the C-ABI: fp16 activations, fp32 norms."""
+"""Path A (Zero123 DDIM / UNet / VAE / CLIP) tensor-level wrappers over the C-ABI: fp16 activations, fp32 norms.
+
+The split-K workspace and the GroupNorm scratch are one buffer per device, handed to the C-ABI by these wrappers (the
+entry points themselves own no memory): calls that may use them must be issued on ONE stream per device at a time, which
+is how the UNet / VAE / CLIP executors run.  Callers that want concurrent streams pass their own workspaces to
+o2345_gemm_f16 / o2345_groupnorm_stats."""
 from __future__ import annotations
 
 import ctypes as C
