@@ -2,8 +2,9 @@
 
 Mirror of reference reconstruction/models/rendering_network.py:26-129 (state-dict keys
 s, ray_dir_fc.{0,2}, base_fc.{0,2}, vis_fc.{0,2}, vis_fc2.{0,2}, rgb_fc.{0,2,4}) and
-reconstruction/models/fields.py:179-185.  The arithmetic of forward() lives in
-csrc/render.cu (render_blend_kernel), fused with the Projector's per-view feature fetch, so
+reconstruction/models/fields.py:179-185.  The arithmetic of forward() lives in csrc/render_tc.cu
+(render_blend_tc_kernel: the per-(sample, view) MLPs as mma.sync chains, default) and csrc/render.cu
+(render_blend_kernel: fp32 FMA, O2345_BLEND_FP32), fused with the Projector's per-view feature fetch, so
 the [n_views, n_rays, n_samples, 59] tensors the reference materialises never exist.
 """
 from __future__ import annotations

@@ -3,7 +3,8 @@
 Mirror of reference reconstruction/models/sparse_sdf_network.py:139-499: same constructor
 arguments, same state-dict keys (compress_layer.*, sparse_costreg_net.conv{0..11}.net.{0,1}.*,
 sdf_layer.lin{0,1,2}.{bias,weight_g,weight_v}), same method signatures and return-dict keys.
-Inference only: the analytic gradient replaces autograd (reference :476-499).
+Inference only: the analytic gradient replaces autograd (reference :476-499).  `sdf` / `gradient` run
+csrc/sdf_mlp_tc.cu (split-fp16 tensor-core GEMMs, fp32-grade values; `ops.SDF_PRECISION`) or csrc/sdf_mlp.cu (fp32 FMA).
 """
 from __future__ import annotations
 
