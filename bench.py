@@ -51,6 +51,7 @@ UNET_FLOP_PER_SAMPLE = 176.3e9
 FLOP_SDF_FWD = 2 * 41856.0
 FLOP_SDF_BWD = 2 * (128 * 144 + 128 * 39)
 RAY_FLOP, RAY_GATHER_BYTES = 211e6, 4.0e6
+PUBLISHED_SEC_PER_MESH = 40.0   # BASELINE.md section 1 (reference README.md:154, A6000, whole run.py)
 
 
 def peaks():
@@ -157,7 +158,10 @@ def run_gpu(args):
         sec_per_mesh = ms * 1e-3 / (args.steps * world)
         out = {"metric": "sec/mesh end-to-end (256x256 in)", "value": sec_per_mesh, "unit": "s/mesh", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": False,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": CONFIG,
+               "scaling": "weak", "vs_baseline": sec_per_mesh / PUBLISHED_SEC_PER_MESH, "dtype": "f16", "data": "synthetic",
+               "config": CONFIG, "baseline_note": "BASELINE.md section 1: 40 s per image for run.py --half_precision on an A6000 "
+                                                  "(reference README.md:154), which also covers SAM, the LoFTR elevation "
+                                                  "search, model loading and a second process start -- not in this step",
                "clocks": clk, "gpu_launches": launches,
                "e2e": {"value": e2e_ms * 1e-3 / (args.steps * world), "unit": "s/mesh", "h2d_bytes_per_step": int(img_host.numel()),
                        "d2h_bytes_per_step": int(mesh["vertices"].nbytes + mesh["triangles"].nbytes + mesh["colors"].nbytes)},
