@@ -103,6 +103,15 @@ def input_image(seed):
     return (S.images(1, H, W, seed=seed)[0].transpose(1, 2, 0) * 255.0).astype(np.uint8)
 
 
+_T0 = time.perf_counter()
+
+
+def beat(msg):
+    """Progress line on stderr (never stdout: ONE JSON line is the contract) so that a stall is attributable."""
+    sys.stderr.write("[bench %7.1f s] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def ev_time(fn):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -113,28 +122,54 @@ def ev_time(fn):
 
 
 def run_gpu(args):
+    """Order of work (each phase announces itself on stderr):  [cpu baseline starts in a child process]  ->  networks  ->
+    warm-up steps  ->  stage breakdown / roofline / rays (untimed extras, BEFORE the timed region so that nothing can
+    stand between the timed loop and the JSON line)  ->  join the cpu baseline  ->  barrier, timed steps, barrier  ->
+    the ONE JSON line, immediately."""
     import torch.distributed as dist
     from o2345 import _lib, sharding, synthetic as S
     from o2345.pipeline import build_networks, image_to_mesh
     from o2345.zero123 import build_zero123
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"bench.py --gpus {args.gpus} was launched with WORLD_SIZE={world}: start it with "
+                         f"`python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py --gpus {args.gpus}`")
+    if args.warmup < 3:
+        beat("note: fewer than 3 warm-up steps requested; the timing rules ask for W >= 3")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_job = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_job = CpuBaselineJob()       # host cores work while the GPU side builds and warms up; joined before the timed region
     if world > 1:
         # keep NCCL's version banner / warnings off stdout: ONE JSON line is the contract
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        beat("process group up: rank %d of %d on cuda:%d" % (rank, world, local))
     tr = build_networks(dev, vol_dim=VOL, states=S.all_states(0), perturb=0.0)
     z123 = build_zero123(dev, seed=0, clip=True).half()   # `--half_precision`: fp16-rounded schedule buffers; CLIP tower attached
     # the only collective on the path: weights from rank 0 over NVLink (no-op at N = 1)
-    sharding.broadcast_module_weights([tr.pyramid_feature_network_geometry_lod0, tr.sdf_network_lod0,
-                                       tr.rendering_network_lod0, tr.variance_network_lod0, z123], src=0)
+    nb = sharding.broadcast_module_weights([tr.pyramid_feature_network_geometry_lod0, tr.sdf_network_lod0,
+                                            tr.rendering_network_lod0, tr.variance_network_lod0, z123], src=0)
+    beat("networks built (%d weight elements broadcast)" % nb)
     img_host = torch.from_numpy(input_image(4321 + rank)).pin_memory()
     step = lambda: image_to_mesh(z123, tr, img_host.numpy(), polar_angle=60, resolution=MESH_RES)
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
+        w = time.perf_counter()
         step()
+        beat("warm-up step %d: %.2f s" % (i, time.perf_counter() - w))
+    torch.cuda.synchronize()
+    pk = peaks()
+    extras = stage_breakdown(z123, tr, dev, pk, world)
+    # every rank renders its own image at the same time: the job's ray throughput is the per-rank rate of the slowest
+    # rank times the number of ranks
+    img_ms = sharding.max_over_ranks([extras["rays"]["image_ms"]], dev)[0]
+    extras["rays"]["image_ms"] = img_ms
+    extras["rays"]["value"] = world * N_RAYS / (img_ms * 1e-3) / 1e6
+    extras["rays"]["n_gpus"] = world
+    cpu = cpu_job.join() if cpu_job is not None else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -145,8 +180,10 @@ def run_gpu(args):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     t0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        w = time.perf_counter()
         mesh = step()
+        beat("timed step %d: %.2f s" % (i, time.perf_counter() - w))
     t1.record()
     torch.cuda.synchronize()
     wall_s = time.perf_counter() - w0
@@ -154,7 +191,6 @@ def run_gpu(args):
     clk = clocks.stop()
     ms, e2e_ms = sharding.max_over_ranks([t0.elapsed_time(t1), wall_s * 1e3], dev)
     if rank == 0:
-        pk = peaks()
         sec_per_mesh = ms * 1e-3 / (args.steps * world)
         out = {"metric": "sec/mesh end-to-end (256x256 in)", "value": sec_per_mesh, "unit": "s/mesh", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": False,
@@ -167,18 +203,52 @@ def run_gpu(args):
                        "d2h_bytes_per_step": int(mesh["vertices"].nbytes + mesh["triangles"].nbytes + mesh["colors"].nbytes)},
                "mesh": {"vertices": int(len(mesh["vertices"])), "triangles": int(len(mesh["triangles"]))},
                "peaks": pk["source"]}
-        out.update(stage_breakdown(z123, tr, dev, pk))
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_reference()
+        out.update(extras)
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
         emit(json.dumps(out))
+        beat("JSON line written")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def stage_breakdown(z123, tr, dev, pk):
+class CpuBaselineJob:
+    """`cpu_baseline` of the main arm: the CPU port timed in a CHILD process (`bench.py --cpu-baseline-child`) that starts
+    with the bench and runs while this process builds the networks and warms the GPU up; it is joined (or, past its
+    deadline, killed and reported as such) before the timed region starts, so it can neither perturb nor delay the
+    timed steps and the JSON line."""
+
+    DEADLINE_S = 300.0
+
+    def __init__(self):
+        self.t0 = time.perf_counter()
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            env.pop(k, None)            # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm uses the host cores
+        env["CUDA_VISIBLE_DEVICES"] = ""
+        self.proc = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-baseline-child"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
+        beat("cpu baseline started in child process %d" % self.proc.pid)
+
+    def join(self):
+        left = self.DEADLINE_S - (time.perf_counter() - self.t0)
+        try:
+            out, _ = self.proc.communicate(timeout=max(left, 1.0))
+            res = json.loads(out.strip().splitlines()[-1])
+            beat("cpu baseline joined: %.0f s/mesh on %d threads" % (res["value"], res["cores"]))
+            return res
+        except Exception as e:   # the baseline is a reported extra: never let it take the bench line down
+            self.proc.kill()
+            beat("cpu baseline unavailable: %r" % (e,))
+            return {"value": None, "unit": "s/mesh", "cores": host_threads(), "kind": "port",
+                    "sample": "unavailable: %s" % type(e).__name__}
+
+
+def stage_breakdown(z123, tr, dev, pk, world=1):
     """Per-stage device times, the tensor-core roofline of the dominant kernel (the tcgen05 GEMM inside the UNet)
-    and the volume-rendering throughput with its own roofline."""
+    and the volume-rendering throughput with its own roofline.  Untimed extras; every rank runs them (symmetric)."""
+    beat("stage breakdown: UNet iteration")
     from o2345 import ops_a
     from o2345.pipeline import synthetic_sample
     unet, vae = z123.model.diffusion_model, z123.first_stage_model
@@ -230,6 +300,7 @@ def stage_breakdown(z123, tr, dev, pk):
     ms_gemm = float(np.median([ev_time(graph.replay)[0] for _ in range(10)]))
     n_gemm = len(rec)
     del graph
+    beat("stage breakdown: %d GEMM launches of one UNet iteration replay in %.3f ms" % (n_gemm, ms_gemm))
     z = torch.randn(4, 4, 32, 32, device=dev)
     vae.decode(z)
     ms_dec = float(np.mean([ev_time(lambda: vae.decode(z))[0] for _ in range(3)]))
@@ -243,6 +314,7 @@ def stage_breakdown(z123, tr, dev, pk):
                         "%.1f GFLOP for the same pass including attention) / CUDA-event time of those launches replayed back to back "
                         "in one CUDA graph (split-K finalize kernels included)" % (flops_counted / 1e9, flops / 1e9)}
     # ---- reconstruction stages + volume rendering
+    beat("stage breakdown: reconstruction + volume rendering")
     sample = synthetic_sample(dev, n_views=N_VIEWS, H=H, W=W)
     tr._conditional_features(sample)
     ms_front, (imgs, fmaps, cond, sizeW, sizeH) = ev_time(lambda: tr._conditional_features(sample))
@@ -322,62 +394,128 @@ def host_threads():
     return max(1, min(os.cpu_count() or 1, 32))
 
 
-def cpu_reference():
-    """The reference's own algorithm on the host cores (oracle/ port, fp32): a bounded sample of every stage of one
-    mesh, extrapolated to the full workload -- 1 UNet iteration at batch 8 (x544), 1 VAE decode of one latent (x40),
-    1 VAE encode (x10), the full 96^3 volume build, and a 48^3 SDF grid (x (256/48)^3)."""
-    from helpers import states_torch
-    from o2345 import synthetic as S
-    from oracle import ldm_oracle as LO, recon_oracle as O, vae_oracle as VO
-    torch.set_num_threads(host_threads())
-    t = lambda x: torch.from_numpy(np.asarray(x)).float()
-    w0 = time.perf_counter()
-    sd_u = {k: torch.from_numpy(v) for k, v in S.unet_state(0).items()}
-    sd_v = {k: torch.from_numpy(v) for k, v in S.vae_state(10).items()}
-    t_setup = time.perf_counter() - w0
-    g = torch.Generator().manual_seed(0)
-    with torch.no_grad():
+class CpuPort:
+    """The reference's own algorithm on the host cores (oracle/ port, fp32): bounded samples of every stage of one mesh,
+    extrapolated to the full workload.  A path-A sample is 1 UNet iteration at batch 8 (x544 per mesh) + 1 VAE decode of
+    one latent (x40) + 1 VAE encode (x10) + 1 CLIP image embedding (x10); a reconstruction sample is the full 96^3 volume
+    build + a 48^3 SDF grid (scaled to 256^3 by the point count) + marching cubes on it (scaled by the cell count) + the
+    colours of 2048 mesh vertices (scaled to the mesh's vertex count, estimated from the 48^3 mesh x (256/48)^2).
+    bench.py is the one place outside tests/ allowed to execute oracle/ (as the CPU baseline, never as the product)."""
+
+    def __init__(self):
+        from helpers import states_torch
+        from o2345 import synthetic as S
+        torch.set_num_threads(host_threads())
+        t = lambda x: torch.from_numpy(np.asarray(x)).float()
         w0 = time.perf_counter()
-        LO.unet_forward(sd_u, torch.randn(8, 8, 32, 32, generator=g), torch.full((8,), 501), torch.randn(8, 1, 768, generator=g))
-        t_unet = time.perf_counter() - w0
-        w0 = time.perf_counter()
-        VO.decode(sd_v, torch.randn(1, 4, 32, 32, generator=g))
-        t_dec = time.perf_counter() - w0
-        w0 = time.perf_counter()
-        VO.encode_moments(sd_v, torch.rand(1, 3, 256, 256, generator=g) * 2 - 1)
-        t_enc = time.perf_counter() - w0
-        from oracle import clip_oracle as CO
-        sd_c = {k: torch.from_numpy(v) for k, v in S.clip_state(20).items()}
-        w0 = time.perf_counter()
-        CO.embed(sd_c, torch.rand(1, 3, 256, 256, generator=g) * 2 - 1)
-        t_clip = time.perf_counter() - w0
-        st = states_torch(0)
+        self.sd_u = {k: torch.from_numpy(v) for k, v in S.unet_state(0).items()}
+        self.sd_v = {k: torch.from_numpy(v) for k, v in S.vae_state(10).items()}
+        self.sd_c = {k: torch.from_numpy(v) for k, v in S.clip_state(20).items()}
+        self.st = states_torch(0)
         cams = S.scene_cameras(S.pose_json(60.0), n_src=N_VIEWS, img_wh=(W, H))
-        imgs = torch.from_numpy(S.images(N_VIEWS + 1, H, W, seed=1234))[1:]
+        self.imgs = torch.from_numpy(S.images(N_VIEWS + 1, H, W, seed=1234))[1:]
+        self.origin, self.proj = t(cams["partial_vol_origin"]), t(cams["affine_mats"])
+        self.w2cs, self.intr = t(cams["w2cs"]), t(cams["intrinsics"])
+        self.t_setup = time.perf_counter() - w0
+        self.g = torch.Generator().manual_seed(0)
+        self.a, self.r = [], []          # per-sample stage times
+
+    @staticmethod
+    def _clock(fn):
         w0 = time.perf_counter()
-        fm = O.pyramid_feature_maps(imgs, st["pyramid_feature_network"])
-        cv = O.conditional_volume(fm, t(cams["partial_vol_origin"]), t(cams["affine_mats"]), st["sdf_network_lod0"], VOL,
-                                  2.0 / (VOL - 1), H, W)
-        t_vol = time.perf_counter() - w0
-        w0 = time.perf_counter()
-        O.sdf_grid(cv["dense"], st["sdf_network_lod0"], 48)
-        t_grid = (time.perf_counter() - w0) * (MESH_RES / 48.0) ** 3
-    total = UNET_ITERS * t_unet + 40 * t_dec + 10 * t_enc + 10 * t_clip + t_vol + t_grid
-    return {"value": total, "unit": "s/mesh", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 UNet iteration at batch 8 ({t_unet:.2f} s, x{UNET_ITERS}) + 1 VAE decode ({t_dec:.2f} s, x40) + 1 VAE encode "
-                      f"({t_enc:.2f} s, x10) + 1 CLIP image embedding ({t_clip:.2f} s, x10) + full 96^3 volume build ({t_vol:.1f} s) + 48^3 SDF grid scaled to 256^3 ({t_grid:.0f} s); "
-                      f"marching cubes / vertex colours not included; weights generated in {t_setup:.0f} s (untimed)"}
+        out = fn()
+        return time.perf_counter() - w0, out
+
+    @torch.no_grad()
+    def path_a_sample(self, record=True):
+        from oracle import clip_oracle as CO, ldm_oracle as LO, vae_oracle as VO
+        g = self.g
+        t_unet, _ = self._clock(lambda: LO.unet_forward(self.sd_u, torch.randn(8, 8, 32, 32, generator=g), torch.full((8,), 501),
+                                                        torch.randn(8, 1, 768, generator=g)))
+        t_dec, _ = self._clock(lambda: VO.decode(self.sd_v, torch.randn(1, 4, 32, 32, generator=g)))
+        t_enc, _ = self._clock(lambda: VO.encode_moments(self.sd_v, torch.rand(1, 3, 256, 256, generator=g) * 2 - 1))
+        t_clip, _ = self._clock(lambda: CO.embed(self.sd_c, torch.rand(1, 3, 256, 256, generator=g) * 2 - 1))
+        if record:
+            self.a.append((t_unet, t_dec, t_enc, t_clip))
+        return t_unet + t_dec + t_enc + t_clip
+
+    @torch.no_grad()
+    def recon_sample(self, record=True):
+        from oracle import recon_oracle as O
+        st = self.st
+
+        def volume():
+            fm = O.pyramid_feature_maps(self.imgs, st["pyramid_feature_network"])
+            return fm, O.conditional_volume(fm, self.origin, self.proj, st["sdf_network_lod0"], VOL, 2.0 / (VOL - 1), H, W)
+        t_vol, (fm, cv) = self._clock(volume)
+        t_grid, u = self._clock(lambda: O.sdf_grid(cv["dense"], st["sdf_network_lod0"], 48))
+        t_mc, (v, tri, _) = self._clock(lambda: O.marching_cubes(u, 0.0))
+        nv = max(len(v), 1)
+        pts = torch.from_numpy(v[np.linspace(0, nv - 1, 2048).astype(np.int64)] / 47.0 * 2 - 1).float() if len(v) else \
+            torch.zeros(2048, 3)
+        t_col, _ = self._clock(lambda: O.vertex_colors(pts, cv["dense"], cv["occ"], fm, self.imgs, self.w2cs, self.intr,
+                                                       st["sdf_network_lod0"], st["rendering_network_lod0"], W=W, H=H))
+        k = MESH_RES / 48.0
+        row = (t_vol, t_grid * k ** 3, t_mc * k ** 3, t_col * (nv * k ** 2) / 2048.0)
+        if record:
+            self.r.append(row)
+        return t_vol + t_grid + t_mc + t_col
+
+    def result(self):
+        med = lambda rows, i: float(np.median([r[i] for r in rows]))
+        tu, td, te, tc = (med(self.a, i) for i in range(4))
+        tv, tg, tm, tcol = (med(self.r, i) for i in range(4))
+        total = UNET_ITERS * tu + 40 * td + 10 * te + 10 * tc + tv + tg + tm + tcol
+        return {"value": total, "unit": "s/mesh", "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"median of {len(self.a)} path-A samples after 1 warm-up: 1 UNet iteration at batch 8 ({tu:.2f} s, x{UNET_ITERS}) + "
+                          f"1 VAE decode ({td:.2f} s, x40) + 1 VAE encode ({te:.2f} s, x10) + 1 CLIP image embedding ({tc:.2f} s, x10); "
+                          f"median of {len(self.r)} reconstruction samples: full 96^3 volume build ({tv:.1f} s) + 48^3 SDF grid scaled to "
+                          f"256^3 ({tg:.0f} s) + marching cubes scaled by cells ({tm:.1f} s) + vertex colours scaled from 2048 vertices "
+                          f"({tcol:.1f} s); weights generated in {self.t_setup:.0f} s (untimed)",
+                "stages_s": {"unet_iteration": tu, "vae_decode": td, "vae_encode": te, "clip_embed": tc, "volume_build": tv,
+                             "sdf_grid_256": tg, "marching_cubes_256": tm, "vertex_colours": tcol}}
+
+
+def cpu_reference(n_a=3, n_recon=1, warm=True):
+    """`cpu_baseline`: 1 warm-up + n_a timed path-A samples, n_recon reconstruction samples (about 30-60 s of host work)."""
+    port = CpuPort()
+    if warm:
+        port.path_a_sample(record=False)
+    for _ in range(n_a):
+        port.path_a_sample()
+    for _ in range(n_recon):
+        port.recon_sample()
+    return port.result()
 
 
 def run_reference(args):
-    """--impl reference: the CPU port of the reference (oracle/) on the host cores, same metric and config."""
+    """--impl reference: the CPU port of the reference (oracle/) on the host cores, same metric and config.  A step is one
+    bounded sample of the workload: a path-A sample every step; a reconstruction sample on the first warm-up step and on
+    (at most) the first 3 timed steps -- W + K steps end within a few minutes.  value = the mesh time extrapolated from
+    the medians of the timed samples."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
-    cb = cpu_reference()
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        if os.environ.get(k) == "1":         # torchrun's default for its workers; this arm owns the host
+            beat("note: %s=1 in the environment; torch.set_num_threads(%d) overrides it for this arm" % (k, host_threads()))
+    port = CpuPort()
+    beat("reference arm: weights ready (%.0f s), %d threads" % (port.t_setup, torch.get_num_threads()))
+    for i in range(args.warmup):
+        dt = port.path_a_sample(record=False) + (port.recon_sample(record=False) if i == 0 else 0.0)
+        beat("reference warm-up sample %d: %.1f s" % (i, dt))
+    w0 = time.perf_counter()
+    for i in range(args.steps):
+        dt = port.path_a_sample() + (port.recon_sample() if i < 3 else 0.0)
+        beat("reference timed sample %d: %.1f s" % (i, dt))
+    wall = time.perf_counter() - w0
+    cb = port.result()
+    cb["timed_samples_wall_s"] = wall
     emit(json.dumps({"impl": "reference", "metric": "sec/mesh end-to-end (256x256 in)", "value": cb["value"], "unit": "s/mesh",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["value"] * 1e3,
                       "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": CONFIG, "cpu_baseline": cb,
+                      "note": "value is one mesh extrapolated from bounded samples (see cpu_baseline.sample); the K timed samples "
+                              "took %.0f s of wall clock" % wall,
                       "e2e": {"value": cb["value"], "unit": "s/mesh", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -403,7 +541,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="o2345", choices=["o2345", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_baseline_child:      # child of CpuBaselineJob: the port's result as one JSON line on stdout
+        return emit(json.dumps(cpu_reference()))
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():

@@ -844,7 +844,14 @@ extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, cons
                                  const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && weight && out, "null pointer");
   O2345_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0 && N > 0, "bad sizes (C must be a multiple of 8)");
-  O2345_CHECK_ARG((128 % W) == 0 || (W % 128) == 0, "image width must divide or be a multiple of the 128-pixel tile");
+  // an output tile is 128 consecutive pixels fetched as ONE box (tw, th, tb): either whole multiples of 128 along a row,
+  // or whole rows that tile the image exactly (H a multiple of 128 / W), or whole images (H * W divides 128).  Any other
+  // shape would wrap a tile across the image border (silently wrong rows) or give a box of fewer than 128 rows (the
+  // stage's byte count would never be reached): refused here, callers take the im2col route.
+  O2345_CHECK_ARG((W % 128) == 0 || ((128 % W) == 0 && (((int64_t)H * W >= 128 && (H % (128 / W)) == 0) ||
+                                                        ((int64_t)H * W < 128 && (128 % (H * W)) == 0))),
+                  "implicit 3x3 conv: the image must tile into 128-pixel boxes (W % 128 == 0, or 128 % W == 0 with "
+                  "H % (128 / W) == 0, or 128 % (H * W) == 0)");
   O2345_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)weight % 16) == 0, "operands must be 16-byte aligned");
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return O2345_ECUDA; }

@@ -131,7 +131,7 @@ class AutoencoderKL(nn.Module):
     def _conv(pk, x, B, H, W, C, conv, gn=None, stride=1, up=False, residual=None, pad_lo=-1, ksize=3):
         g = None if gn is None else A.groupnorm_stats(x, B, H * W, C, 32, gn.eps, *pk.norm(gn))
         w, b = pk.conv(conv)
-        if ksize == 3 and stride == 1 and not up and pad_lo < 0 and A.conv3x3_supported(W, C):
+        if ksize == 3 and stride == 1 and not up and pad_lo < 0 and A.conv3x3_supported(H, W, C):
             a = x if g is None else A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, True)[0]
             return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual), H, W
         a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, ksize, stride, up, g, gn is not None and ksize == 3, pad_lo=pad_lo)

@@ -207,8 +207,16 @@ def conv3x3(x, B, H, W, C, weight, bias=None, residual=None, act=0, out_dtype=_f
     return out
 
 
-def conv3x3_supported(W, C):
-    return C % 8 == 0 and C >= 64 and (128 % W == 0 or W % 128 == 0)
+def conv3x3_supported(H, W, C):
+    """Shapes the implicit 3x3 conv takes (the same rule o2345_conv3x3_f16 enforces): a 128-pixel output tile must be one
+    TMA box of whole row segments / whole rows / whole images.  Everything else goes through norm_act_im2col + gemm."""
+    if C % 8 or C < 64:
+        return False
+    if W % 128 == 0:
+        return True
+    if 128 % W:
+        return False
+    return (H % (128 // W) == 0) if H * W >= 128 else (128 % (H * W) == 0)
 
 
 def clip_patches(x, res, patch, mean, std, kp):

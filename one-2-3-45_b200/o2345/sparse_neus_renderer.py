@@ -46,15 +46,21 @@ class SparseNeuSRenderer(nn.Module):
 
     # ------------------------------------------------------------------ helpers
     def _source_views(self, feature_maps, color_maps, w2cs, intrinsics, img_wh):
-        key = (feature_maps.data_ptr(), feature_maps._version, color_maps.data_ptr(), color_maps._version,
-               w2cs.data_ptr(), w2cs._version, intrinsics.data_ptr())
-        if key != self._views_key:
+        """Channel-last source maps + projection matrices, rebuilt whenever any input is a different tensor OBJECT or has
+        been written to.  The cache holds strong references to the inputs it was built from: an address can only be
+        re-used by the caching allocator after the tensor is gone, so identity + version cannot alias a new scene
+        (keying on data_ptr alone could: a second image in the same process may land on the first one's address)."""
+        ins = (feature_maps, color_maps, w2cs, intrinsics)
+        key = self._views_key
+        same = key is not None and all(a is b for a, b in zip(key[0], ins)) and key[1] == tuple(t._version for t in ins) \
+            and key[2] == (float(img_wh[0]), float(img_wh[1]))
+        if not same:
             maps = source_maps_channel_last(feature_maps, color_maps)
             w2cs_f, intr = w2cs.float(), intrinsics.float()
             proj = torch.matmul(intr, w2cs_f[:, :3, :])
             centers = torch.inverse(w2cs_f)[:, :3, 3]
             self._views = ops.SourceViews(maps, proj, centers, float(img_wh[0]), float(img_wh[1]))
-            self._views_key = key
+            self._views_key = (ins, tuple(t._version for t in ins), (float(img_wh[0]), float(img_wh[1])))
         return self._views
 
     def _u_table(self, n, dev):

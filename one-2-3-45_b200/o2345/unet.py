@@ -200,7 +200,7 @@ class UNetModel(nn.Module):
     def _conv3(self, pk, x, B, H, W, C, conv, gn=None, act=False, stride=1, up=False, residual=None, rowbias=None):
         g = None if gn is None else A.groupnorm_stats(x, B, H * W, C, 32, gn.eps, *pk.norm(gn))
         w, b = pk.conv(conv)
-        if stride == 1 and not up and A.conv3x3_supported(W, C):
+        if stride == 1 and not up and A.conv3x3_supported(H, W, C):
             # implicit GEMM: normalise once ([M, C], not 9x) and let TMA fetch the nine shifted windows
             a = x if g is None else A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, act)[0]
             return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual, rowbias=rowbias), H, W
@@ -337,7 +337,7 @@ class UNetModel(nn.Module):
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """Epsilon prediction.  On CUDA the ~525 kernel launches of one pass are captured once per input shape in a
         CUDA graph and replayed (the pass is launch-bound from Python: 18 ms eager vs the device time of the graph);
-        the returned tensor is the graph's static output buffer and is overwritten by the next call."""
+        the returned tensor is a copy of the graph's static output buffer."""
         assert y is None, "the Zero123 UNet is not class-conditional"
         self._ensure_context(context)
         if not (self.use_cuda_graph and x.is_cuda) or torch.cuda.is_current_stream_capturing():
@@ -358,7 +358,9 @@ class UNetModel(nn.Module):
         sx.copy_(x), st.copy_(timesteps), sc.copy_(context)
         graph.replay()
         _lib.add_launches(n_kernels)
-        return out
+        # a fresh tensor, as the reference returns: the graph's static output buffer is overwritten by the next call, and
+        # code written for the reference keeps eps across calls (e_t = apply_model(x, t, c); e_uc = apply_model(x, t, uc))
+        return out.clone()
 
     @torch.no_grad()
     def _forward_impl(self, x, timesteps, context):
