@@ -32,7 +32,8 @@ extern "C" {
 #define O2345_ECUDA (-2)
 #define O2345_EUNSUPPORTED (-3)
 
-#define O2345_ABI_VERSION 2   /* 2: o2345_epilogue, precision arguments of sdf_query / render_blend, GroupNorm as affine */
+#define O2345_ABI_VERSION 3   /* 2: o2345_epilogue, precision arguments of sdf_query / render_blend, GroupNorm as affine
+                                 3: split-K tickets inside the workspace (no finalize kernel), o2345_last_trap, o2345_debug_gemm_force */
 
 typedef void* o2345_stream_t;
 
@@ -284,9 +285,21 @@ int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, i
                    int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
                    int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const o2345_epilogue* ep /* NULL: plain */,
                    float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
-/* splitk_ws (optional, may be NULL): fp32 scratch of ws_floats >= M*N elements that is ALL ZERO on entry; when the output
- * tiles alone cannot fill the GPU the K range is split over several CTAs per tile that accumulate into it, and a finalize
- * kernel applies the epilogue and leaves it zeroed again. */
+/* splitk_ws (optional, may be NULL): fp32 scratch of ws_floats elements.  Its last 4096 words hold per-tile tickets and must
+ * be ZERO on entry (they are left zero); the rest holds up to floor((ws_floats - 4096) / (M*N)) private partial planes and
+ * needs no initialisation.  When the output tiles alone cannot fill the GPU the K range is split over several CTAs per
+ * tile; each stores its partial tile in its own plane and the last CTA of a tile to arrive sums the planes and applies the
+ * epilogue.  One workspace serves one stream at a time. */
+
+/* Every mbarrier wait inside the GEMM kernel is bounded (4 s).  If one expires the kernel records which barrier of which CTA
+ * of which problem stalled in a host-mapped buffer and traps (the CUDA context then reports a launch failure at the next
+ * synchronisation).  o2345_last_trap copies a description of that record into buf and returns 1, or returns 0 if no wait
+ * has ever expired in this process.  Safe to call after the context has failed. */
+int o2345_last_trap(char* buf, size_t n);
+
+/* Tuning hook (tools/gemm_sweep.py; not part of the data path): force the tile configuration of the following non-batched
+ * GEMM / conv calls: ctas in {1, 2}, bn in {64, 128, 160, 256}, splits >= 1; 0 keeps the heuristic's choice of that field. */
+void o2345_debug_gemm_force(int ctas, int bn, int splits);
 
 /* Diagnostic hook (not part of the data path): when device_buf16 != NULL, CTA (0,0,0) of every following CTA-pair GEMM
  * launch stores clock64() stamps of its phases into device_buf16[0..8] (entry, prologue done, first TMA issued, last TMA

@@ -1,24 +1,34 @@
 // fp16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM accumulators), operands fed by TMA.
-// Path A of SURVEY.md section 8 (rows A2-A4, A6): every Linear / 1x1 conv / 3x3 conv of the Zero123 UNet and the
-// VAE, and the QK^T / PV products of the unfused attention fallback, go through this file.
+// Path A of SURVEY.md section 8 (rows A2-A4, A6, A8): every Linear / 1x1 conv / 3x3 conv of the Zero123 UNet, the VAE and
+// the CLIP tower, and the QK^T / PV products of the unfused attention fallback, go through this file.
 //
 //   C[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T + bias[N] + rowbias[row / rpg, N] ) (+ residual[M,N])   fp16 in, fp32 acc
 //
 // A and B are both K-major (row-major activations [rows, K]; nn.Linear / flattened conv weights [N, K]).
 //
-// Main kernel (gemm2): a CTA PAIR (cluster of 2 on one TPC) computes a 256 x BN output tile with
-// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the B tile, the tensor cores of both SMs
-// read both halves, so the L2 -> SM operand traffic per flop is 100-128 flop/B instead of the 64 flop/B of a lone 128 x 128
-// tile (r1 ncu: the single-CTA kernel was L2-bandwidth bound at 3-600 TFLOP/s).  Per CTA:
-//   warp 0     TMA producer: cp.async.bulk.tensor (cta_group::2 form: completes on the LEADER's mbarrier), SWIZZLE_128B,
-//              into a multi-stage shared-memory ring guarded by full (leader) / empty (both CTAs, multicast commit) mbarriers;
-//   warp 1     allocates TMEM for the pair; in the leader CTA one lane issues tcgen05.mma (M=256, N=BN, K=16) four
-//              times per stage, committing each stage back to both producers and the finished accumulator to both epilogues;
-//   warps 2-5  epilogue on the CTA's own 128 accumulator rows: tcgen05.ld (32 lanes x 32 columns) -> bias / row-group bias /
-//              activation / GEGLU gate / residual in registers -> fp16 or fp32 stores (rows past M, columns past N masked;
-//              TMA zero-fills the K, M and N tails on the way in).
-// Two pairs are co-resident per SM pair (<= 104 KB smem, <= 256 TMEM columns each), so one tile's prologue / epilogue
-// overlaps the other's main loop.  The single-CTA kernel (gemm1) remains for N <= 64 and for the 4-D batched (per-head) mode.
+// ONE kernel template, gemm_tc_kernel<BN, STAGES, CTAS, MODE> (round 1 had two hand-copied kernels):
+//   CTAS = 2  a CTA PAIR (cluster of 2 on one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages
+//             its own 128 rows of A and HALF of the B tile, the tensor cores of both SMs read both halves (100-128 flop per
+//             operand byte instead of 64 for a lone 128 x 128 tile; the L2 -> SM fabric is the binding resource);
+//   CTAS = 1  a single CTA computes 128 x BN (M <= 128, and the 4-D batched per-head mode).
+// Warp roles (320 threads, two CTAs resident per SM so that one tile's prologue / epilogue overlaps the other's main loop):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B) into a STAGES-deep shared-memory ring guarded by full /
+//               empty mbarriers (pair: the bytes of both CTAs are counted on the leader's full barrier, stages are freed in
+//               both CTAs by a multicast tcgen05.commit);
+//   warp 1      allocates TMEM; one lane (of the leader) issues tcgen05.mma M = 128 * CTAS, N = BN, K = 16, four per stage;
+//   warps 2-9   EIGHT epilogue warps (round 1: four): warp w owns TMEM lane quarter w % 4 (a hardware rule) and one of two
+//               column ranges of the tile.  While the main loop runs they stage bias / row-group bias in shared memory and
+//               PREFETCH THE RESIDUAL into registers (round 1 fetched it after the accumulator was complete: 2 400 - 6 000
+//               cycles of exposed latency per tile); then tcgen05.ld -> alpha / bias / activation / GEGLU gate -> fp16 ->
+//               a shared-memory transpose in the idle operand ring -> coalesced row stores with the residual added.
+// MODE selects the epilogue at compile time (round 1 inlined every variant into one 9 600-instruction body):
+//   0 staged, no activation   1 staged, GEGLU gate   2 staged, SiLU / GELU / QuickGELU (runtime switch per tile)
+//   3 generic (fp32 output, batched, unaligned N) and SPLIT-K.
+// Split-K (tiles alone cannot fill 148 SMs): each of the `splits` CTAs of a tile stores its partial accumulator into its own
+// fp32 plane of the workspace and takes a ticket; the LAST one to arrive sums the planes, applies the epilogue and zeroes the
+// ticket (round 1 added into one plane with L2 atomics and launched a second kernel: 92 extra launches per UNet iteration).
+// Every mbarrier wait is bounded in TIME (4 s): a protocol bug or a lost arrival records which barrier of which CTA of
+// which problem stalled in a host-visible buffer (o2345_last_trap) and traps, instead of spinning for tens of minutes.
 #include <cuda.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
@@ -29,9 +39,21 @@ namespace o2345 {
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int GEMM_THREADS = 192;
-constexpr uint32_t SPIN_LIMIT = 1u << 28;  // bounded waits: a protocol bug traps instead of hanging the GPU
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: "the even CTA of my pair"
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;
+constexpr uint64_t WAIT_LIMIT_NS = 4000000000ull;   // bounded waits: a protocol bug traps (with a record) instead of hanging the GPU
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;         // clears the CTA-rank bit of a shared::cluster address: "the even CTA of my pair"
+constexpr int TICKET_INTS = 4096;                   // split-K tickets live in the last TICKET_INTS words of the workspace
+constexpr int RES_PREFETCH = 8;                     // 16-byte residual pieces per lane fetched before the accumulator is ready
+
+enum { WAIT_EMPTY = 1, WAIT_FULL = 2, WAIT_ACC = 3 };   // which wait timed out (o2345_last_trap)
+
+struct TrapRecord {
+  unsigned long long magic;
+  int tag, stage, bx, by, bz, rank, M, N, K, bn, ctas, mode, splits, conv;
+};
+constexpr unsigned long long TRAP_MAGIC = 0x6f32333435545250ull;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -41,18 +63,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!done && ++spins > SPIN_LIMIT) __trap();
-  }
+__device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -87,6 +112,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight epilogue warps only
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4,
 // LBO = 1 (ignored for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1, layout type 2.
@@ -103,30 +129,32 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+template <int CTAS>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CTAS == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
-__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// pair: arrives on the barrier at this shared-memory offset in BOTH CTAs once the pair's MMAs so far have finished
+template <int CTAS>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the pair's MMAs so far have finished
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
-      ::"r"(smem_u32(bar))
-      : "memory");
+  if (CTAS == 2)
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -161,16 +189,41 @@ struct GemmParams {
   // 4-D tensor map (C, W, H, B); an output tile of 128 consecutive pixels is a box (64 ch, tw, th, tb), and kernel tap
   // (ky, kx) is the same box shifted by (kx-1, ky-1) -- TMA's out-of-bounds zero fill IS the convolution padding.
   int conv, cC, cH, cW, cblocks;
-  // split-K for shapes that cannot fill the GPU with output tiles (M <= 2048 with K up to 23 040): `splits` CTAs per
-  // tile accumulate with fp32 reductions into ws [M, N] (zero on entry), a second kernel applies the epilogue and re-zeroes.
+  // split-K: CTA z of a tile stores its partial accumulator in plane z of ws [splits, M, N]; the last CTA of a tile to take
+  // its ticket sums the planes and applies the epilogue (tickets: zero on entry, left zero).
   int splits;
   float* ws;
-  int staged;                  // fp16 output through a shared-memory transpose so that global stores are coalesced rows
+  int* tickets;
+  // GroupNorm statistics of the OUTPUT (staged modes): colstats[g * N + col] += x and colstats[(groups + g) * N + col] += x^2
+  // of the final fp16 values of row group g = row / stats_rpg (the consumer turns them into mean / rstd); nullptr: off
+  float* colstats;
+  int stats_rpg, stats_groups;
   long long* trace;            // diagnostic: CTA (0,0,0) stores clock64() stamps of its phases (o2345_debug_gemm_trace), else nullptr
+  TrapRecord* diag;            // host-mapped record written before a bounded wait traps (may be nullptr)
+  int bn, ctas, mode;          // for the trap record
 };
 
 __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
   if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = clock64();
+}
+
+__device__ __noinline__ void wait_timed_out(const GemmParams& p, int tag, int stage) {
+  if (p.diag) {
+    TrapRecord* d = p.diag;
+    d->tag = tag, d->stage = stage, d->bx = blockIdx.x, d->by = blockIdx.y, d->bz = blockIdx.z, d->rank = (int)cluster_ctarank();
+    d->M = p.M, d->N = p.N, d->K = p.K, d->bn = p.bn, d->ctas = p.ctas, d->mode = p.mode, d->splits = p.splits, d->conv = p.conv;
+    __threadfence_system();
+    d->magic = TRAP_MAGIC;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const GemmParams& p, int tag, int stage) {
+  if (mbar_try(bar, parity)) return;
+  const uint64_t t0 = global_ns();
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity))
+    if (((++spins) & 255u) == 0 && global_ns() - t0 > WAIT_LIMIT_NS) wait_timed_out(p, tag, stage);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -194,25 +247,9 @@ __device__ __forceinline__ void store8(const GemmParams& p, int64_t off, const f
   }
 }
 
-// One thread's 32 consecutive accumulator columns [col0, col0 + 32) of output row `row` (crow = element offset of the row
-// in C / residual): everything after the MMA.
+// Generic epilogue (MODE 3, one pass): one thread's 32 consecutive accumulator columns [col0, col0 + 32) of output row
+// `row` (crow = element offset of the row in C / residual), stored straight from registers.
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int row, int64_t crow, int col0) {
-  if (p.splits > 1) {  // partial tile: fp32 reductions into the workspace, epilogue applied by splitk_finalize
-    float* w = p.ws + (int64_t)row * p.N + col0;
-    if ((p.N & 3) == 0) {
-#pragma unroll
-      for (int e = 0; e < 32; e += 4)
-        if (col0 + e < p.N)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(w + e), "f"(__uint_as_float(r[e])),
-                       "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])), "f"(__uint_as_float(r[e + 3]))
-                       : "memory");
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (col0 + e < p.N) atomicAdd(w + e, __uint_as_float(r[e]));
-    }
-    return;
-  }
   const __half* rb = p.rowbias ? p.rowbias + (int64_t)(row / p.rows_per_group) * p.rowbias_ld : nullptr;
   if (p.act == 3) {  // GEGLU: 16 values then their 16 gates; N is a multiple of 32 (checked on the host)
     if (col0 >= p.N) return;
@@ -271,27 +308,136 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
+// split-K, every CTA: one thread's 32 accumulator columns of one row go to THIS split's private fp32 partial plane
+// ws[split][M][N] with plain vector stores (round 1 and the first round-2 version added into one shared plane with
+// red.global.add.f32: the L2 atomic units sustain only ~90 G elements/s, 35-60 us for a 2 M element output)
+__device__ __forceinline__ void splitk_partial(const GemmParams& p, const uint32_t (&r)[32], int split, int row, int col0) {
+  float* w = p.ws + ((int64_t)split * p.M + row) * p.N + col0;
+  if ((p.N & 3) == 0) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4)
+      if (col0 + e < p.N)
+        __stcg(reinterpret_cast<float4*>(w + e), make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                              __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (col0 + e < p.N) __stcg(w + e, __uint_as_float(r[e]));
+  }
+}
+
+// split-K, the LAST CTA of a tile to take its ticket: out = act(alpha * sum_s ws[s] + bias + rowbias) + residual over the
+// CTA's 128 x BN block.  te = 0..255 (the epilogue threads): one thread per (row, 8 columns) when N and ldc allow 16-byte
+// accesses, else one per element.  The partials were written by other SMs: reads bypass L1; two pieces x two splits are in
+// flight per thread (8 x 16 bytes), enough to cover the L2 round trip at the SM's ingest rate.
+template <int BN>
+__device__ __forceinline__ void splitk_finalize(const GemmParams& p, int m0, int n0, int te) {
+  const bool vec = (p.N % 8) == 0 && (p.ldc % 8) == 0 && (!p.rowbias || (p.rowbias_ld % 8) == 0);
+  const int64_t plane = (int64_t)p.M * p.N;
+  if (vec) {
+    constexpr int PPR = BN / 8;
+    constexpr int NP = BM * PPR;
+    for (int i = te; i < NP; i += 2 * EPI_THREADS) {
+      float v[2][8];
+      int64_t woff[2];
+      bool ok[2];
+      int rowq[2], colq[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ii = i + u * EPI_THREADS;
+        const int rl = ii / PPR;
+        rowq[u] = m0 + rl, colq[u] = n0 + (ii - rl * PPR) * 8;
+        ok[u] = ii < NP && rowq[u] < p.M && colq[u] < p.N;
+        woff[u] = (int64_t)rowq[u] * p.N + colq[u];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+      }
+      for (int s = 0; s < p.splits; s += 2) {
+        float4 a[2][2], b[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const bool on = ok[u] && s + t < p.splits;
+            const float4* w = reinterpret_cast<const float4*>(p.ws + (int64_t)(s + t) * plane + woff[u]);
+            a[u][t] = on ? __ldcg(w) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b[u][t] = on ? __ldcg(w + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            v[u][0] += a[u][t].x, v[u][1] += a[u][t].y, v[u][2] += a[u][t].z, v[u][3] += a[u][t].w;
+            v[u][4] += b[u][t].x, v[u][5] += b[u][t].y, v[u][6] += b[u][t].z, v[u][7] += b[u][t].w;
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        const int row = rowq[u], col = colq[u];
+        const int64_t o = (int64_t)row * p.ldc + col;
+        if (p.rowbias) {
+          uint4 q = *reinterpret_cast<const uint4*>(p.rowbias + (int64_t)(row / p.rows_per_group) * p.rowbias_ld + col);
+          const __half* h = reinterpret_cast<const __half*>(&q);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[u][e] = fmaf(v[u][e], p.alpha, __half2float(h[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[u][e] *= p.alpha;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (p.bias) v[u][e] += __ldg(p.bias + col + e);
+          v[u][e] = apply_act(v[u][e], p.act);
+        }
+        if (p.residual) {
+          uint4 q = *reinterpret_cast<const uint4*>(p.residual + o);
+          const __half* h = reinterpret_cast<const __half*>(&q);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[u][e] += __half2float(h[e]);
+        }
+        store8(p, o, v[u]);
+      }
+    }
+    return;
+  }
+  for (int i = te; i < BM * BN; i += EPI_THREADS) {
+    const int rl = i / BN, row = m0 + rl, col = n0 + (i - rl * BN);
+    if (row >= p.M || col >= p.N) continue;
+    float x = 0.f;
+    for (int s = 0; s < p.splits; ++s) x += __ldcg(p.ws + (int64_t)s * plane + (int64_t)row * p.N + col);
+    x *= p.alpha;
+    if (p.rowbias) x += __half2float(p.rowbias[(int64_t)(row / p.rows_per_group) * p.rowbias_ld + col]);
+    if (p.bias) x += __ldg(p.bias + col);
+    x = apply_act(x, p.act);
+    const int64_t o = (int64_t)row * p.ldc + col;
+    if (p.residual) x += __half2float(p.residual[o]);
+    if (p.out_f32) reinterpret_cast<float*>(p.C)[o] = x;
+    else reinterpret_cast<__half*>(p.C)[o] = __float2half_rn(x);
+  }
+}
+
 constexpr int EPI_RB_GROUPS = 8;                 // row-bias groups (images) one 128-row tile may span when staged in smem
 constexpr int epi_smem_bytes(int bn) { return bn * 4 + EPI_RB_GROUPS * bn * 2; }
+// the two column ranges of the eight epilogue warps split the tile at a multiple of 32 (a GEGLU chunk never straddles them)
+__host__ __device__ constexpr int col_split(int bn) { return ((bn / 2 + 31) / 32) * 32; }
 
-// Called by the four epilogue warps while the main loop runs: the tile's bias and row-group-bias slices go to shared
-// memory, so that the epilogue proper never waits on a first-touch global load (r1 trace: five serialized L2 misses).
+// Called by the eight epilogue warps while the main loop runs: the tile's bias and row-group-bias slices go to shared
+// memory, so that the epilogue proper never waits on a first-touch global load.
 template <int BN>
-__device__ __forceinline__ void epilogue_preload(const GemmParams& p, int m0, int n0, float* sbias, __half* srb, int tid_e) {
-  if (p.splits <= 1) {
-    for (int i = tid_e; i < BN; i += 128) sbias[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-    if (p.rowbias) {
-      const int g0 = m0 / p.rows_per_group;
-      const int last = (m0 + BM - 1 < p.M ? m0 + BM - 1 : p.M - 1) / p.rows_per_group;
-      const int ng = last - g0 + 1;
-      if (ng >= 1 && ng <= EPI_RB_GROUPS)
-        for (int i = tid_e; i < ng * BN; i += 128) {
-          const int gi = i / BN, c = i - gi * BN;
-          srb[i] = (n0 + c < p.N) ? p.rowbias[(int64_t)(g0 + gi) * p.rowbias_ld + n0 + c] : __float2half(0.f);
-        }
-    }
+__device__ __forceinline__ void epilogue_preload(const GemmParams& p, int m0, int n0, float* sbias, __half* srb, int te) {
+  for (int i = te; i < BN; i += EPI_THREADS) sbias[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+  if (p.rowbias) {
+    const int g0 = m0 / p.rows_per_group;
+    const int last = (m0 + BM - 1 < p.M ? m0 + BM - 1 : p.M - 1) / p.rows_per_group;
+    const int ng = last - g0 + 1;
+    if (ng >= 1 && ng <= EPI_RB_GROUPS)
+      for (int i = te; i < ng * BN; i += EPI_THREADS) {
+        const int gi = i / BN, c = i - gi * BN;
+        srb[i] = (n0 + c < p.N) ? p.rowbias[(int64_t)(g0 + gi) * p.rowbias_ld + n0 + c] : __float2half(0.f);
+      }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+  epi_bar();
 }
 
 template <int ACT>
@@ -302,13 +448,14 @@ __device__ __forceinline__ float act_fn(float x) {
   return x;
 }
 
-// Phase 1 of the staged epilogue for one thread (= one accumulator row): TMEM -> registers -> alpha / bias / row-group
-// bias / activation (ACT 3: GEGLU gate) -> fp16 -> this row of the warp's shared-memory slab.
-template <int BN, int ACT>
-__device__ __forceinline__ void stage_rows(const GemmParams& p, uint32_t tmem_row_base, uint8_t* mine, int n0, const float* sbias,
-                                           const __half* rb, bool rb_smem) {
+// Phase 1 of the staged epilogue for one thread (= one accumulator row) over tile columns [c_lo, c_hi): TMEM -> registers ->
+// alpha / bias / row-group bias / activation (ACT 3: GEGLU gate) -> fp16 -> this row of the warp's shared-memory slab.
+// rb: this row's row-group bias indexed by TILE column (nullptr: none); rb_smem: it is the shared-memory copy (no N tail).
+template <int ACT>
+__device__ __forceinline__ void stage_rows(const GemmParams& p, uint32_t tmem_row_base, uint8_t* mine, int n0, int c_lo, int c_hi,
+                                           const float* sbias, const __half* rb, bool rb_smem) {
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
     uint32_t r[32];
     tmem_ld32(tmem_row_base + c0, r);
     if (n0 + c0 >= p.N) break;                     // warp-uniform
@@ -321,7 +468,7 @@ __device__ __forceinline__ void stage_rows(const GemmParams& p, uint32_t tmem_ro
         float g1 = fmaf(__uint_as_float(r[17 + e]), p.alpha, sbias[c0 + 17 + e]);
         h[e >> 1] = __floats2half2_rn(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
       }
-      uint4* d = reinterpret_cast<uint4*>(mine + (c0 >> 1) * 2);
+      uint4* d = reinterpret_cast<uint4*>(mine + (c0 - c_lo));   // (c0 - c_lo) / 2 output columns x 2 bytes
       d[0] = reinterpret_cast<uint4*>(h)[0], d[1] = reinterpret_cast<uint4*>(h)[1];
     } else {
 #pragma unroll
@@ -341,224 +488,168 @@ __device__ __forceinline__ void stage_rows(const GemmParams& p, uint32_t tmem_ro
           float x0 = fmaf(__uint_as_float(r[j + e]), p.alpha, v[e]), x1 = fmaf(__uint_as_float(r[j + e + 1]), p.alpha, v[e + 1]);
           h[e >> 1] = __floats2half2_rn(act_fn<ACT>(x0), act_fn<ACT>(x1));
         }
-        *reinterpret_cast<uint4*>(mine + (c0 + j) * 2) = *reinterpret_cast<uint4*>(h);
+        *reinterpret_cast<uint4*>(mine + (c0 - c_lo + j) * 2) = *reinterpret_cast<uint4*>(h);
       }
     }
   }
 }
 
-// Staged epilogue of one warp's 32 accumulator rows x BN columns (fp16 output).  Phase 1: thread = row, as the TMEM
-// load delivers it: alpha / bias / row-group bias / activation / GEGLU gate, rounded to fp16 (where autocast rounds the
-// layer output) into this warp's slab of the (now idle) operand ring.  Phase 2: the warp walks the slab in 16-byte
-// pieces along rows, adds the residual and writes whole rows: every global access is a run of full 32-byte sectors, and
-// the residual loads of four pieces are in flight together.
-// (r1 trace: with one 16-byte store per lane to 32 different rows the epilogue took 46 000 cycles per tile, 10x the
-// main loop of a K = 320 GEMM.)
-template <int BN>
-__device__ __forceinline__ void epilogue_staged(const GemmParams& p, uint32_t tmem_row_base, uint8_t* slab, int lane, int m0,
-                                                int row0, int n0, const float* sbias, const __half* srb) {
-  const bool geglu = p.act == 3;
-  const int outc = geglu ? BN / 2 : BN;           // output columns of this tile
-  const int stride = outc * 2 + 16;               // bytes per staged row (+16: 16-byte pieces of consecutive rows rotate banks)
+// Output geometry of one epilogue warp in the staged modes: 32 rows x tile columns [c_lo, c_hi) become `outc` fp16 columns
+// (GEGLU halves them) = `ppr` 16-byte pieces per row, `total` pieces per warp, lane l owns pieces l, l + 32, ...
+struct WarpOut {
+  int outc, stride, ppr, total, ocol0, nout;
+};
+template <int MODE>
+__device__ __forceinline__ WarpOut warp_out(const GemmParams& p, int n0, int c_lo, int c_hi) {
+  constexpr bool geglu = MODE == 1;
+  WarpOut g;
+  g.outc = geglu ? (c_hi - c_lo) >> 1 : (c_hi - c_lo);
+  g.stride = g.outc * 2 + 16;                      // +16: 16-byte pieces of consecutive rows rotate banks
+  g.ppr = g.outc >> 3;
+  g.total = 32 * g.ppr;
+  g.ocol0 = geglu ? (n0 + c_lo) >> 1 : n0 + c_lo;  // first column of C this warp writes
+  g.nout = geglu ? p.N >> 1 : p.N;
+  return g;
+}
+
+// The first RES_PREFETCH residual pieces of this lane, fetched while the main loop runs.
+__device__ __forceinline__ void prefetch_residual(const GemmParams& p, const WarpOut& g, int lane, int row0,
+                                                  uint4 (&resq)[RES_PREFETCH]) {
+#pragma unroll
+  for (int u = 0; u < RES_PREFETCH; ++u) {
+    resq[u] = make_uint4(0u, 0u, 0u, 0u);
+    const int pp = lane + 32 * u;
+    if (p.residual && pp < g.total) {
+      const int rl = pp / g.ppr, ci = pp - rl * g.ppr;
+      const int grow = row0 + rl, col = g.ocol0 + ci * 8;
+      if (grow < p.M && col < g.nout) resq[u] = *reinterpret_cast<const uint4*>(p.residual + (int64_t)grow * p.ldc + col);
+    }
+  }
+}
+
+__device__ __forceinline__ uint4 add_h8(uint4 v, uint4 q) {
+  __half2* a = reinterpret_cast<__half2*>(&v);
+  const __half2* b = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 fa = __half22float2(a[e]), fb = __half22float2(b[e]);
+    a[e] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+  }
+  return v;
+}
+
+// Staged epilogue of ONE warp: 32 accumulator rows (its TMEM lane quarter) x tile columns [c_lo, c_hi), fp16 output.
+//   phase 1   thread = row, as the TMEM load delivers it: alpha / bias / row-group bias / activation / GEGLU gate, rounded to
+//             fp16 (where autocast rounds the layer output) into this warp's slab of the (now idle) operand ring;
+//   phase 2   the warp walks the slab in 16-byte pieces along rows, adds the residual (prefetched for the first
+//             RES_PREFETCH pieces of a lane) and writes whole rows: every global access is a run of full 32-byte sectors.
+// (r1 trace: with one 16-byte store per lane to 32 different rows the epilogue took 46 000 cycles per tile.)
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_staged(const GemmParams& p, const WarpOut& g, uint32_t tmem_row_base, uint8_t* slab, int lane,
+                                                int m0, int row0, int n0, int c_lo, int c_hi, const float* sbias, const __half* srb,
+                                                const uint4 (&resq)[RES_PREFETCH]) {
   const int row = row0 + lane;
   // row-group bias of this thread's row: from the smem copy when the tile spans few groups, else straight from global
   const __half* rb = nullptr;
   bool rb_smem = false;
-  if (p.rowbias) {
+  if (MODE != 1 && p.rowbias) {
     const int rr = row < p.M ? row : p.M - 1;
     const int g0 = m0 / p.rows_per_group, last = (m0 + BM - 1 < p.M ? m0 + BM - 1 : p.M - 1) / p.rows_per_group;
     rb_smem = last - g0 + 1 <= EPI_RB_GROUPS;
     rb = rb_smem ? srb + (rr / p.rows_per_group - g0) * BN : p.rowbias + (int64_t)(rr / p.rows_per_group) * p.rowbias_ld + n0;
   }
-  uint8_t* mine = slab + lane * stride;
-  // the activation switch is hoisted out of the element loops: one branch per tile instead of two per element
-  switch (p.act) {
-    case 1: stage_rows<BN, 1>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
-    case 2: stage_rows<BN, 2>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
-    case 3: stage_rows<BN, 3>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
-    case 4: stage_rows<BN, 4>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
-    default: stage_rows<BN, 0>(p, tmem_row_base, mine, n0, sbias, rb, rb_smem); break;
+  uint8_t* mine = slab + lane * g.stride;
+  if (MODE == 0) {
+    stage_rows<0>(p, tmem_row_base, mine, n0, c_lo, c_hi, sbias, rb, rb_smem);
+  } else if (MODE == 1) {
+    stage_rows<3>(p, tmem_row_base, mine, n0, c_lo, c_hi, sbias, rb, rb_smem);
+  } else {   // the activation switch is hoisted out of the element loops: one branch per tile
+    switch (p.act) {
+      case 1: stage_rows<1>(p, tmem_row_base, mine, n0, c_lo, c_hi, sbias, rb, rb_smem); break;
+      case 2: stage_rows<2>(p, tmem_row_base, mine, n0, c_lo, c_hi, sbias, rb, rb_smem); break;
+      default: stage_rows<4>(p, tmem_row_base, mine, n0, c_lo, c_hi, sbias, rb, rb_smem); break;
+    }
   }
   __syncwarp();
-  const int ppr = outc >> 3;                       // 16-byte pieces per row
-  const int total = 32 * ppr;
-  const int nout = geglu ? p.N >> 1 : p.N, n0out = geglu ? n0 >> 1 : n0;
   __half* C = reinterpret_cast<__half*>(p.C);
+  // N is a multiple of 8 on this path (host check): no partial pieces
+#pragma unroll
+  for (int u = 0; u < RES_PREFETCH; ++u) {
+    const int pp = lane + 32 * u;
+    if (pp < g.total) {
+      const int rl = pp / g.ppr, ci = pp - rl * g.ppr;
+      const int grow = row0 + rl, col = g.ocol0 + ci * 8;
+      if (grow < p.M && col < g.nout) {
+        uint4 v = *reinterpret_cast<const uint4*>(slab + rl * g.stride + ci * 16);
+        if (p.residual) v = add_h8(v, resq[u]);
+        *reinterpret_cast<uint4*>(C + (int64_t)grow * p.ldc + col) = v;
+      }
+    }
+  }
   constexpr int UN = 4;
-  for (int base = lane; base < total; base += 32 * UN) {
+  for (int base = lane + 32 * RES_PREFETCH; base < g.total; base += 32 * UN) {
     uint4 v[UN], q[UN];
     int64_t o[UN];
     bool ok[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int pp = base + 32 * u;
-      const int rl = pp / ppr, ci = pp - rl * ppr;
-      const int grow = row0 + rl, col = n0out + ci * 8;
-      ok[u] = pp < total && grow < p.M && col < nout;   // N is a multiple of 8 on this path (host check): no partial pieces
+      const int rl = pp / g.ppr, ci = pp - rl * g.ppr;
+      const int grow = row0 + rl, col = g.ocol0 + ci * 8;
+      ok[u] = pp < g.total && grow < p.M && col < g.nout;
       o[u] = (int64_t)grow * p.ldc + col;
       if (ok[u]) {
-        v[u] = *reinterpret_cast<const uint4*>(slab + rl * stride + ci * 16);
+        v[u] = *reinterpret_cast<const uint4*>(slab + rl * g.stride + ci * 16);
         if (p.residual) q[u] = *reinterpret_cast<const uint4*>(p.residual + o[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       if (!ok[u]) continue;
-      if (p.residual) {
-        __half2* a = reinterpret_cast<__half2*>(&v[u]);
-        const __half2* b = reinterpret_cast<const __half2*>(&q[u]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 fa = __half22float2(a[e]), fb = __half22float2(b[e]);
-          a[e] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
-        }
-      }
+      if (p.residual) v[u] = add_h8(v[u], q[u]);
       *reinterpret_cast<uint4*>(C + o[u]) = v[u];
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------ single-CTA kernel
-template <int BN, int STAGES>
+__host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : bn <= 256 ? 256 : 512; }
+__host__ __device__ constexpr int epi_slab_bytes(int bn) { return EPI_WARPS * 32 * (col_split(bn) * 2 + 16); }
+constexpr int smem_bytes(int bn, int stages, int ctas) {
+  return stages * (BM * BK * 2 + (bn / ctas) * BK * 2) + (2 * stages + 1) * 8 + 8 + 16 + epi_smem_bytes(bn) + 1024;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int BN, int STAGES, int CTAS, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-gemm_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);
-  __half* srb = reinterpret_cast<__half*>(sbias + BN);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, bz = blockIdx.z;
-  const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
-  // split-K: blockIdx.z owns k-blocks [kb0, kb1) and adds its partial tile into the fp32 workspace
-  int kb0 = 0, kb1 = nk;
-  if (p.splits > 1) {
-    kb0 = (int)((int64_t)nk * bz / p.splits);
-    kb1 = (int)((int64_t)nk * (bz + 1) / p.splits);
-  }
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
-    mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {  // TMEM: BN fp32 columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // everything above touched no global memory: it overlaps the tail of the previous kernel
-  pdl_trigger();
-
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer
-      for (int kb = kb0; kb < kb1; ++kb) {
-        int s = (kb - kb0) % STAGES;
-        uint32_t ph = ((kb - kb0) / STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
-        mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-        if (p.conv) {
-          const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
-          const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
-          tma_load_4d(sA + s * A_BYTES, &tmA, full + s, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
-          tma_load_2d(sB + s * B_BYTES, &tmB, full + s, tap * p.cC + c0, n0);
-        } else if (p.batched) {
-          tma_load_4d(sA + s * A_BYTES, &tmA, full + s, kb * BK, m0, bz % p.nh, bz / p.nh);
-          tma_load_4d(sB + s * B_BYTES, &tmB, full + s, kb * BK, n0, bz % p.nh, bz / p.nh);
-        } else {
-          tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * BK, m0);
-          tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * BK, n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        int s = (kb - kb0) % STAGES;
-        uint32_t ph = ((kb - kb0) / STAGES) & 1;
-        mbar_wait(full + s, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advancing 16 fp16 along K inside the 128-byte swizzle atom = +32 bytes on the start address
-          umma_f16(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, ((kb - kb0) | k) != 0);
-        }
-        umma_commit(empty + s);   // frees the smem stage once these MMAs have read it
-      }
-      umma_commit(tmem_full);     // accumulator complete
-    }
-  } else {  // ------------------------ epilogue warps 2..5, TMEM lane quarter = warp % 4
-    const int quarter = warp & 3;
-    if (p.staged) epilogue_preload<BN>(p, m0, n0, sbias, srb, threadIdx.x - 64);
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + quarter * 32 + lane;
-    if (p.staged) {   // operand ring is idle once the accumulator is complete: reuse it for the output transpose
-      epilogue_staged<BN>(p, tmem_base + ((uint32_t)(quarter * 32) << 16), smem + quarter * 32 * (BN * 2 + 16), lane, m0,
-                          m0 + quarter * 32, n0, sbias, srb);
-    } else {
-      const int64_t crow = (p.batched ? (int64_t)(bz % p.nh) * p.stride_c_h + (int64_t)(bz / p.nh) * p.stride_c_b : 0) +
-                           (int64_t)row * p.ldc;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-        if (row < p.M) epilogue_chunk(p, r, row, crow, n0 + c0);
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ CTA-pair kernel
-__host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : bn <= 256 ? 256 : 512; }
-
-template <int BN, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 2)
-gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int BH = BN / 2;                                  // rows of B staged by each CTA of the pair
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BH * BK * 2;
+  constexpr int BROWS = BN / CTAS;                           // rows of B staged by this CTA (pair: half of the tile)
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BROWS * BK * 2;
   static_assert(B_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "tile width: a multiple of 32 (GEGLU chunks, 32-column TMEM loads)");
+  static_assert(epi_slab_bytes(BN) <= STAGES * (A_BYTES + B_BYTES), "the output transpose must fit in the operand ring");
   constexpr int TCOLS = tmem_cols(BN);
+  constexpr int CSPLIT = col_split(BN);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);   // [0] TMEM base address, [1] split-K "this CTA is the last"
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~(uintptr_t)15);
   __half* srb = reinterpret_cast<__half*>(sbias + BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) stamp(p, 0);
-  const uint32_t rank = cluster_ctarank();                    // 0 = leader (issues the MMAs, owns the full barriers)
-  const int m0 = (blockIdx.x >> 1) * (2 * BM) + (int)rank * BM, n0 = blockIdx.y * BN, bz = blockIdx.z;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs, owns the full barriers)
+  const int m0 = CTAS == 2 ? (blockIdx.x >> 1) * (2 * BM) + (int)rank * BM : blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN, bz = blockIdx.z;
   const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
+  // split-K: blockIdx.z owns k-blocks [kb0, kb1) and adds its partial tile into the fp32 workspace
   int kb0 = 0, kb1 = nk;
-  if (p.splits > 1) {
+  if (MODE == 3 && p.splits > 1) {
     kb0 = (int)((int64_t)nk * bz / p.splits);
     kb1 = (int)((int64_t)nk * (bz + 1) / p.splits);
   }
@@ -571,12 +662,18 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {  // the same warp of BOTH CTAs allocates the pair's TMEM columns
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TCOLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  if (warp == 1) {  // TMEM: TCOLS fp32 columns x 128 lanes (pair: the same warp of BOTH CTAs allocates the pair's columns)
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TCOLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TCOLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  cluster_sync_all();   // barrier inits of the leader must be visible before the peer's TMA can complete on them
+  if (CTAS == 2) cluster_sync_all();   // barrier inits of the leader must be visible before the peer's TMA can complete on them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // everything above touched no global memory: it overlaps the tail of the previous kernel
@@ -584,74 +681,128 @@ gemm2_f16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (threadIdx.x == 0) stamp(p, 1);
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer (both CTAs): own 128 rows of A, own half of the B tile
+    if (lane == 0) {  // ---------------- TMA producer: own 128 rows of A, own BROWS rows of the B tile
       for (int kb = kb0; kb < kb1; ++kb) {
-        int s = (kb - kb0) % STAGES;
-        uint32_t ph = ((kb - kb0) / STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
-        if (rank == 0) mbar_expect_tx(full + s, 2 * (A_BYTES + B_BYTES));   // the peer's bytes land on this barrier too
-        const int nb = n0 + (int)rank * BH;
-        if (p.conv) {
-          const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
-          const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
-          tma2_load_4d(sA + s * A_BYTES, &tmA, full + s, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
-          tma2_load_2d(sB + s * B_BYTES, &tmB, full + s, tap * p.cC + c0, nb);
+        const int s = (kb - kb0) % STAGES;
+        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1, p, WAIT_EMPTY, s);
+        uint8_t* a_dst = sA + s * A_BYTES;
+        uint8_t* b_dst = sB + s * B_BYTES;
+        if (CTAS == 2) {
+          if (rank == 0) mbar_expect_tx(full + s, 2 * (A_BYTES + B_BYTES));   // the peer's bytes land on this barrier too
+          const int nb = n0 + (int)rank * BROWS;
+          if (p.conv) {
+            const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
+            const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
+            tma2_load_4d(a_dst, &tmA, full + s, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+            tma2_load_2d(b_dst, &tmB, full + s, tap * p.cC + c0, nb);
+          } else {
+            tma2_load_2d(a_dst, &tmA, full + s, kb * BK, m0);
+            tma2_load_2d(b_dst, &tmB, full + s, kb * BK, nb);
+          }
         } else {
-          tma2_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * BK, m0);
-          tma2_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * BK, nb);
+          mbar_expect_tx(full + s, A_BYTES + B_BYTES);
+          if (p.conv) {
+            const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
+            const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
+            tma_load_4d(a_dst, &tmA, full + s, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+            tma_load_2d(b_dst, &tmB, full + s, tap * p.cC + c0, n0);
+          } else if (p.batched) {
+            tma_load_4d(a_dst, &tmA, full + s, kb * BK, m0, bz % p.nh, bz / p.nh);
+            tma_load_4d(b_dst, &tmB, full + s, kb * BK, n0, bz % p.nh, bz / p.nh);
+          } else {
+            tma_load_2d(a_dst, &tmA, full + s, kb * BK, m0);
+            tma_load_2d(b_dst, &tmB, full + s, kb * BK, n0);
+          }
         }
         if (kb == kb0) stamp(p, 2);
       }
       stamp(p, 3);
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {  // ---------------- MMA issuer (leader only): M = 256 across the pair
-      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+    if (lane == 0 && rank == 0) {  // ---------------- MMA issuer (pair: the leader only, M = 256 across the pair)
+      constexpr uint32_t idesc = umma_idesc_f16(CTAS * BM, BN);
       for (int kb = kb0; kb < kb1; ++kb) {
-        int s = (kb - kb0) % STAGES;
-        uint32_t ph = ((kb - kb0) / STAGES) & 1;
-        mbar_wait(full + s, ph);
+        const int s = (kb - kb0) % STAGES;
+        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
+        mbar_wait(full + s, ph, p, WAIT_FULL, s);
         if (kb == kb0) stamp(p, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
+        const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma2_f16(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, ((kb - kb0) | k) != 0);
-        umma2_commit(empty + s);   // frees this stage in both CTAs
+        for (int k = 0; k < BK / 16; ++k)   // advancing 16 fp16 along K inside the 128-byte swizzle atom = +32 bytes on the start address
+          umma_f16<CTAS>(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, ((kb - kb0) | k) != 0);
+        umma_commit<CTAS>(empty + s);   // frees this stage (pair: in both CTAs) once these MMAs have read it
       }
-      umma2_commit(tmem_full);     // accumulator complete: both epilogues may start
+      umma_commit<CTAS>(tmem_full);     // accumulator complete: the epilogue warps (pair: of both CTAs) may start
       stamp(p, 5);
     }
-  } else {  // ------------------------ epilogue warps 2..5 on this CTA's 128 accumulator rows
-    const int quarter = warp & 3;
-    if (p.staged) epilogue_preload<BN>(p, m0, n0, sbias, srb, threadIdx.x - 64);
-    mbar_wait(tmem_full, 0);
-    if (threadIdx.x == 64) stamp(p, 6);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + quarter * 32 + lane;
-    if (p.staged) {   // operand ring is idle once the accumulator is complete: reuse it for the output transpose
-      epilogue_staged<BN>(p, tmem_base + ((uint32_t)(quarter * 32) << 16), smem + quarter * 32 * (BN * 2 + 16), lane, m0,
-                          m0 + quarter * 32, n0, sbias, srb);
+  } else {  // ------------------------ epilogue warps 2..9 on this CTA's 128 accumulator rows
+    const int e = warp - 2, quarter = warp & 3, te = threadIdx.x - 64;
+    const int c_lo = e < 4 ? 0 : CSPLIT, c_hi = e < 4 ? CSPLIT : BN;   // this warp's tile columns
+    const int row0 = m0 + quarter * 32;
+    const uint32_t tmem_row_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    if (MODE != 3) {
+      epilogue_preload<BN>(p, m0, n0, sbias, srb, te);
+      const WarpOut g = warp_out<MODE>(p, n0, c_lo, c_hi);
+      uint4 resq[RES_PREFETCH];
+      prefetch_residual(p, g, lane, row0, resq);
+      mbar_wait(tmem_full, 0, p, WAIT_ACC, 0);
+      if (threadIdx.x == 64) stamp(p, 6);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // the operand ring is idle once the accumulator is complete: it becomes the output transpose buffer
+      epilogue_staged<BN, MODE>(p, g, tmem_row_base, smem + e * 32 * (CSPLIT * 2 + 16), lane, m0, row0, n0, c_lo, c_hi, sbias, srb, resq);
     } else {
-      const int64_t crow = (int64_t)row * p.ldc;
+      mbar_wait(tmem_full, 0, p, WAIT_ACC, 0);
+      if (threadIdx.x == 64) stamp(p, 6);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = row0 + lane;
+      if (p.splits > 1) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
-        if (row < p.M) epilogue_chunk(p, r, row, crow, n0 + c0);
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_row_base + c0, r);
+          if (row < p.M) splitk_partial(p, r, bz, row, n0 + c0);
+        }
+        __threadfence();                 // this thread's partial sums are visible before the CTA takes its ticket
+        epi_bar();
+        if (te == 0) {
+          int* tk = p.tickets + (blockIdx.y * gridDim.x + blockIdx.x);
+          const int last = atomicAdd(tk, 1) == p.splits - 1;
+          if (last) atomicExch(tk, 0);   // left zeroed for the next launch
+          tmem_slot[1] = (uint32_t)last;
+        }
+        epi_bar();
+        if (tmem_slot[1]) {
+          __threadfence();
+          splitk_finalize<BN>(p, m0, n0, te);
+        }
+      } else {
+        const int64_t crow = (p.batched ? (int64_t)(bz % p.nh) * p.stride_c_h + (int64_t)(bz / p.nh) * p.stride_c_b : 0) +
+                             (int64_t)row * p.ldc;
+#pragma unroll 1
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_row_base + c0, r);
+          if (row < p.M) epilogue_chunk(p, r, row, crow, n0 + c0);
+        }
       }
     }
     if (threadIdx.x == 64) stamp(p, 7);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or the peer's TMEM reads are in flight
+  // pair: neither CTA may free TMEM / exit while the pair's MMAs or the peer's TMEM reads are in flight
+  if (CTAS == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
   }
   if (threadIdx.x == 0) stamp(p, 8);
 }
 
+// ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -684,136 +835,152 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int64_t l
   return O2345_OK;
 }
 
-// split-K epilogue: out = act(alpha * ws + bias + rowbias) + residual, and ws is left zeroed for the next call.
-// One thread per (row, 8 columns) when N and ldc allow 16-byte accesses, else one per element.
-__global__ void splitk_finalize_kernel(GemmParams p, int vec) {
-  pdl_wait();
-  pdl_trigger();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (vec) {
-    const int n8 = p.N >> 3;
-    if (i >= p.M * n8) return;
-    const int row = i / n8, col = (i - row * n8) << 3;
-    float4* w = reinterpret_cast<float4*>(p.ws + (int64_t)row * p.N + col);
-    float4 a = w[0], b = w[1];
-    w[0] = make_float4(0.f, 0.f, 0.f, 0.f), w[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    const int64_t o = (int64_t)row * p.ldc + col;
-    if (p.rowbias) {
-      uint4 q = *reinterpret_cast<const uint4*>(p.rowbias + (int64_t)(row / p.rows_per_group) * p.rowbias_ld + col);
-      const __half* h = reinterpret_cast<const __half*>(&q);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], p.alpha, __half2float(h[e]));
+// Host-mapped trap record (one per process): allocated on the first launch that is not inside a stream capture.
+TrapRecord* g_diag = nullptr;
+bool g_diag_tried = false;
+TrapRecord* diag_buffer(cudaStream_t st) {
+  if (!g_diag_tried) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return g_diag;
+    }
+    g_diag_tried = true;
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(TrapRecord), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      memset(h, 0, sizeof(TrapRecord));
+      g_diag = reinterpret_cast<TrapRecord*>(h);
     } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+      cudaGetLastError();
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (p.bias) v[e] += __ldg(p.bias + col + e);
-      v[e] = apply_act(v[e], p.act);
-    }
-    if (p.residual) {
-      uint4 q = *reinterpret_cast<const uint4*>(p.residual + o);
-      const __half* h = reinterpret_cast<const __half*>(&q);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] += __half2float(h[e]);
-    }
-    store8(p, o, v);
-    return;
   }
-  if (i >= p.M * p.N) return;
-  const int row = i / p.N, col = i - row * p.N;
-  float x = p.ws[i] * p.alpha;
-  p.ws[i] = 0.f;
-  if (p.rowbias) x += __half2float(p.rowbias[(int64_t)(row / p.rows_per_group) * p.rowbias_ld + col]);
-  if (p.bias) x += __ldg(p.bias + col);
-  x = apply_act(x, p.act);
-  int64_t o = (int64_t)row * p.ldc + col;
-  if (p.residual) x += __half2float(p.residual[o]);
-  if (p.out_f32) reinterpret_cast<float*>(p.C)[o] = x;
-  else reinterpret_cast<__half*>(p.C)[o] = __float2half_rn(x);
+  return g_diag;
 }
 
-// how many k-splits for a non-batched problem whose output tiles give `ctas` CTAs: fill ~2 CTAs per SM, keep >= 4 k-blocks
-// per split
-int pick_splits(const GemmParams& p, int ctas, float* ws, int64_t ws_floats) {
-  static int min_kb = -1;
-  if (min_kb < 0) {   // k-blocks each split must keep (tuning knob; the default is the measured optimum of the UNet pass)
+struct Config {
+  int ctas, bn, splits;
+};
+
+// tuning / sweep hook: O2345_GEMM_FORCE="ctas,bn,splits" (0 = keep the heuristic's choice for that field); also settable
+// through o2345_debug_gemm_force (tools/gemm_sweep.py)
+int g_force[3] = {-1, 0, 0};
+void read_force_env() {
+  if (g_force[0] >= 0) return;
+  g_force[0] = g_force[1] = g_force[2] = 0;
+  const char* e = getenv("O2345_GEMM_FORCE");
+  if (e) sscanf(e, "%d,%d,%d", &g_force[0], &g_force[1], &g_force[2]);
+}
+
+int min_kblocks_per_split() {
+  static int v = -1;
+  if (v < 0) {   // k-blocks each split must keep (tuning knob)
     const char* e = getenv("O2345_SPLITK_MIN_KB");
-    min_kb = e ? atoi(e) : 12;   // r1 sweep of the UNet pass: 4 -> 5.20 ms, 8 -> 5.03, 12 -> 4.98, 16 -> 5.01, 24 -> 5.11
-    if (min_kb < 1) min_kb = 1;
+    v = e ? atoi(e) : 8;
+    if (v < 1) v = 1;
   }
-  if (!ws || p.batched || p.act == 3 || (int64_t)p.M * p.N > ws_floats) return 1;
-  int nk = p.conv ? 9 * p.cblocks : cdiv(p.K, BK);
-  if (ctas >= 120 || nk < 2 * min_kb) return 1;
-  int s = 2 * sm_count() / ctas;
-  if (s > nk / min_kb) s = nk / min_kb;
-  if (s > 32) s = 32;
-  return s < 2 ? 1 : s;
+  return v;
 }
 
-// coalesced (shared-memory staged) epilogue: fp16 output, whole 16-byte pieces, one pass (no split-K, no head batches)
-void pick_staged(GemmParams& p) {
+// Tile shape and k-splits for a problem of M x N with nk k-blocks of 64.  The resource to fill is 148 SMs x 2 resident
+// CTAs; per-tile fixed cost (prologue, first TMA round trip, epilogue, tear-down) is ~4 us, so small problems want many
+// small tiles and long-K problems with few tiles want split-K; large problems want the widest tile (operand traffic).
+Config pick_config(const GemmParams& p, int nk, bool can_split, int64_t ws_floats) {
+  read_force_env();
+  Config c;
+  const int M = p.M, N = p.N;
+  if (p.batched) {
+    c.ctas = 1, c.bn = N <= 64 ? 64 : 128, c.splits = 1;
+    return c;
+  }
+  c.ctas = M <= BM ? 1 : 2;
+  if (c.ctas == 1) {
+    c.bn = N <= 64 ? 64 : 128;
+  } else {
+    if (N <= 64) c.bn = 64;
+    else if (N % 160 == 0) c.bn = 160;
+    else if (N <= 128) c.bn = 128;
+    else c.bn = (N % 256 == 0 || N > 640) ? 256 : (N % 128 == 0 ? 128 : 160);
+    // few tiles and a short K: halve the tile width so that more SMs share the (latency-bound) work
+    const int tiles = 2 * cdiv(M, 2 * BM) * cdiv(N, c.bn);
+    if (tiles < sm_count() / 2 && nk <= 24 && c.bn > 64 && N % 64 == 0) c.bn = 64;
+  }
+  if (g_force[0] == 1 || g_force[0] == 2) c.ctas = g_force[0];
+  if (g_force[1] == 64 || g_force[1] == 128 || (c.ctas == 2 && (g_force[1] == 160 || g_force[1] == 256))) c.bn = g_force[1];
+  if (c.ctas == 1 && c.bn > 128) c.bn = 128;
+  const int mblocks = c.ctas == 2 ? 2 * cdiv(M, 2 * BM) : cdiv(M, BM);
+  const int ctas_total = mblocks * cdiv(N, c.bn);
+  c.splits = 1;
+  if (can_split && p.act != 3 && p.ws && 2 * (int64_t)M * N <= ws_floats - TICKET_INTS && ctas_total <= TICKET_INTS) {
+    const int max_planes = (int)((ws_floats - TICKET_INTS) / ((int64_t)M * N));
+    const int min_kb = min_kblocks_per_split();
+    if (ctas_total < 120 && nk >= 2 * min_kb) {
+      int s = 2 * sm_count() / ctas_total;
+      if (s > nk / min_kb) s = nk / min_kb;
+      if (s > 32) s = 32;
+      c.splits = s < 2 ? 1 : s;
+    }
+    if (g_force[2] > 0) c.splits = g_force[2] > nk ? nk : g_force[2];
+    if (c.splits > max_planes) c.splits = max_planes;
+  }
+  return c;
+}
+
+// which compile-time epilogue: staged fp16 output needs whole 16-byte pieces and one pass (no split-K, no head batches)
+int pick_mode(const GemmParams& p, const Config& c) {
   const int nout = p.act == 3 ? p.N / 2 : p.N;
-  p.staged = !p.out_f32 && p.splits <= 1 && !p.batched && (nout % 8) == 0 && (p.ldc % 8) == 0 && ((uintptr_t)p.C % 16) == 0 &&
-             (!p.residual || ((uintptr_t)p.residual % 16) == 0);
-}
-
-int finalize(const GemmParams& p, cudaStream_t st) {
-  if (p.splits <= 1) return O2345_OK;
-  const int vec = (p.N % 8) == 0 && (p.ldc % 8) == 0 && (!p.rowbias || (p.rowbias_ld % 8) == 0);
-  const int64_t n = vec ? (int64_t)p.M * (p.N / 8) : (int64_t)p.M * p.N;
-  O2345_CUDA(launch_pdl(splitk_finalize_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), st, p, vec));
-  O2345_LAUNCH_CHECK();
-  return O2345_OK;
-}
-
-template <int BN, int STAGES>
-int launch1(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + epi_smem_bytes(BN) + 1024;
-  static PerDeviceOnce attr;
-  if (attr.need()) {
-    O2345_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  }
-  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), batch > 0 ? batch : (p.splits > 1 ? p.splits : 1));
-  O2345_CUDA(launch_pdl(gemm_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), (size_t)(SMEM), st, a, b, p));
-  O2345_LAUNCH_CHECK();
-  return finalize(p, st);
-}
-
-template <int BN, int STAGES>
-int launch2(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 1) * 8 + 16 + epi_smem_bytes(BN) + 1024;
-  static PerDeviceOnce attr;
-  if (attr.need()) {
-    O2345_CUDA(cudaFuncSetAttribute(gemm2_f16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  }
-  dim3 grid(2 * cdiv(p.M, 2 * BM), cdiv(p.N, BN), p.splits > 1 ? p.splits : 1);
-  O2345_CUDA(launch_pdl(gemm2_f16_tc_kernel<BN, STAGES>, dim3(grid), dim3(GEMM_THREADS), (size_t)(SMEM), st, a, b, p));
-  O2345_LAUNCH_CHECK();
-  return finalize(p, st);
-}
-
-// tile width of the CTA-pair kernel for an N-column problem: 160 divides every UNet width (320 k), else 256 / 128
-int pick_bn2(int N) {
-  static int n256 = -1;
-  if (n256 < 0) {   // widths from which a multiple of 256 takes the 256-wide tile instead of 160 (tuning knob)
-    const char* e = getenv("O2345_BN256_MIN_N");
-    n256 = e ? atoi(e) : (1 << 30);   // r1 sweep of the UNet pass: off 4.99 ms, N >= 2560 -> 5.06, N >= 1280 -> 5.23: 160 stays
-  }
-  if (N <= 64) return 0;          // single-CTA kernel with BN = 64
-  if (N % 256 == 0 && N >= n256) return 256;
-  if (N % 160 == 0) return 160;
-  if (N <= 128) return 128;
-  return N % 256 == 0 || N > 640 ? 256 : (N % 128 == 0 ? 128 : 160);
+  const bool staged = !p.out_f32 && c.splits <= 1 && !p.batched && (nout % 8) == 0 && (p.ldc % 8) == 0 && ((uintptr_t)p.C % 16) == 0 &&
+                      (!p.residual || ((uintptr_t)p.residual % 16) == 0) && !(c.ctas == 1 && p.act == 3);
+  if (!staged) return 3;
+  return p.act == 0 ? 0 : (p.act == 3 ? 1 : 2);
 }
 
 long long* g_trace = nullptr;
 
+template <int BN, int STAGES, int CTAS, int MODE>
+int launch(const CUtensorMap& a, const CUtensorMap& b, GemmParams p, int batch, cudaStream_t st) {
+  constexpr int SMEM = smem_bytes(BN, STAGES, CTAS);
+  static_assert(2 * SMEM <= 227 * 1024 + 2048, "two CTAs per SM");
+  static PerDeviceOnce attr;
+  if (attr.need()) {
+    O2345_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  }
+  p.bn = BN, p.ctas = CTAS, p.mode = MODE;
+  p.diag = diag_buffer(st);
+  const int mblocks = CTAS == 2 ? 2 * cdiv(p.M, 2 * BM) : cdiv(p.M, BM);
+  dim3 grid(mblocks, cdiv(p.N, BN), batch > 0 ? batch : (p.splits > 1 ? p.splits : 1));
+  O2345_CUDA(launch_pdl_cluster(gemm_tc_kernel<BN, STAGES, CTAS, MODE>, grid, dim3(GEMM_THREADS), (size_t)SMEM, st, CTAS, a, b, p));
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+template <int BN, int STAGES, int CTAS>
+int launch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
+  switch (mode) {
+    case 0: return launch<BN, STAGES, CTAS, 0>(a, b, p, batch, st);
+    case 1:
+      if constexpr (CTAS == 2) return launch<BN, STAGES, 2, 1>(a, b, p, batch, st);
+      else return launch<BN, STAGES, CTAS, 3>(a, b, p, batch, st);
+    case 2: return launch<BN, STAGES, CTAS, 2>(a, b, p, batch, st);
+    default: return launch<BN, STAGES, CTAS, 3>(a, b, p, batch, st);
+  }
+}
+
+int dispatch(const Config& c, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
+  if (c.ctas == 2) {
+    if (c.bn == 64) return launch_mode<64, 5, 2>(mode, a, b, p, batch, st);
+    if (c.bn == 128) return launch_mode<128, 4, 2>(mode, a, b, p, batch, st);
+    if (c.bn == 160) return launch_mode<160, 4, 2>(mode, a, b, p, batch, st);
+    return launch_mode<256, 3, 2>(mode, a, b, p, batch, st);
+  }
+  if (c.bn == 64) return launch_mode<64, 4, 1>(mode, a, b, p, batch, st);
+  return launch_mode<128, 3, 1>(mode, a, b, p, batch, st);
+}
+
 int fill_epilogue(GemmParams& p, const o2345_epilogue* ep, int M, int N, int64_t ldc) {
   p.bias = nullptr, p.rowbias = nullptr, p.rowbias_ld = 0, p.rows_per_group = 1, p.residual = nullptr;
   p.out_f32 = 0, p.act = 0, p.alpha = 1.f, p.trace = g_trace;
+  p.colstats = nullptr, p.stats_rpg = 1, p.stats_groups = 0;
+  p.diag = nullptr, p.bn = p.ctas = p.mode = 0;
   if (!ep) return O2345_OK;
   O2345_CHECK_ARG(ep->act >= 0 && ep->act <= 4, "unknown activation");
   O2345_CHECK_ARG(!ep->rowbias || (ep->rows_per_group > 0 && (ep->rowbias_ld % 8) == 0 && ((uintptr_t)ep->rowbias % 16) == 0),
@@ -827,10 +994,10 @@ int fill_epilogue(GemmParams& p, const o2345_epilogue* ep, int M, int N, int64_t
   return O2345_OK;
 }
 
-int dispatch2(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-  if (bn == 160) return launch2<160, 4>(ma, mb, p, st);
-  if (bn == 256) return launch2<256, 3>(ma, mb, p, st);
-  return launch2<128, 4>(ma, mb, p, st);
+void set_workspace(GemmParams& p, float* ws, int64_t ws_floats) {
+  p.ws = ws;
+  p.tickets = (ws && ws_floats > TICKET_INTS) ? reinterpret_cast<int*>(ws + (ws_floats - TICKET_INTS)) : nullptr;
+  if (!p.tickets) p.ws = nullptr;
 }
 
 }  // namespace
@@ -839,6 +1006,25 @@ int dispatch2(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmPa
 using namespace o2345;
 
 extern "C" void o2345_debug_gemm_trace(long long* device_buf16) { g_trace = device_buf16; }
+
+extern "C" void o2345_debug_gemm_force(int ctas, int bn, int splits) {
+  g_force[0] = ctas, g_force[1] = bn, g_force[2] = splits;
+}
+
+extern "C" int o2345_last_trap(char* buf, size_t n) {
+  if (!buf || n == 0) return O2345_EINVAL;
+  buf[0] = 0;
+  const TrapRecord* d = g_diag;
+  if (!d || d->magic != TRAP_MAGIC) return 0;
+  static const char* names[] = {"?", "empty (producer waiting for the MMA to free a stage)", "full (MMA issuer waiting for TMA bytes)",
+                                "accumulator (epilogue waiting for the last MMA)"};
+  snprintf(buf, n,
+           "gemm_tc_kernel<BN=%d, CTAS=%d, MODE=%d> M=%d N=%d K=%d conv=%d splits=%d: CTA (%d,%d,%d) rank %d gave up after 4 s "
+           "on barrier '%s' stage %d",
+           d->bn, d->ctas, d->mode, d->M, d->N, d->K, d->conv, d->splits, d->bx, d->by, d->bz, d->rank,
+           names[d->tag >= 1 && d->tag <= 3 ? d->tag : 0], d->stage);
+  return 1;
+}
 
 extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
                                  const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream) {
@@ -874,21 +1060,13 @@ extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, cons
   int rc = fill_epilogue(p, ep, p.M, N, ldc);
   if (rc) return rc;
   p.batched = 0, p.conv = 1, p.cC = C, p.cH = H, p.cW = W, p.cblocks = (C + BK - 1) / BK;
-  p.ws = splitk_ws;
+  set_workspace(p, splitk_ws, ws_floats);
   cudaStream_t st = (cudaStream_t)stream;
-  const int bn = pick_bn2(N);
-  if (bn == 0) {
-    rc = make_map(&mb, weight, N, 9 * (int64_t)C, 9 * (int64_t)C, 0, 0, 0, 0, 64);
-    if (rc) return rc;
-    p.splits = pick_splits(p, cdiv(p.M, BM), splitk_ws, ws_floats);
-    pick_staged(p);
-    return launch1<64, 4>(ma, mb, p, 0, st);
-  }
-  rc = make_map(&mb, weight, N, 9 * (int64_t)C, 9 * (int64_t)C, 0, 0, 0, 0, bn / 2);
+  const Config c = pick_config(p, 9 * p.cblocks, true, ws_floats);
+  p.splits = c.splits;
+  rc = make_map(&mb, weight, N, 9 * (int64_t)C, 9 * (int64_t)C, 0, 0, 0, 0, c.bn / c.ctas);
   if (rc) return rc;
-  p.splits = pick_splits(p, 2 * cdiv(p.M, 2 * BM) * cdiv(N, bn), splitk_ws, ws_floats);
-  pick_staged(p);
-  return dispatch2(bn, ma, mb, p, st);
+  return dispatch(c, pick_mode(p, c), ma, mb, p, 0, st);
 }
 
 extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
@@ -908,25 +1086,14 @@ extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int 
   O2345_CHECK_ARG(nh == 0 || (!p.rowbias && p.act != 3), "row bias / GEGLU are not available in batched mode");
   p.batched = nh > 0 ? 1 : 0;
   p.conv = 0, p.cC = p.cH = p.cW = p.cblocks = 0;
-  p.ws = splitk_ws;
+  set_workspace(p, splitk_ws, ws_floats);
   cudaStream_t st = (cudaStream_t)stream;
+  const Config c = pick_config(p, cdiv(K, BK), nh == 0, ws_floats);
+  p.splits = c.splits;
   CUtensorMap ma, mb;
   rc = make_map(&ma, A, M, K, lda, nh, nb, stride_a_h, stride_a_b, BM);
   if (rc) return rc;
-  const int bn = nh > 0 ? 0 : pick_bn2(N);
-  if (bn == 0) {  // single-CTA kernel: per-head batches and N <= 64
-    const int BN1 = N <= 64 ? 64 : 128;
-    rc = make_map(&mb, B, N, K, ldb, nh, nb, stride_b_h, stride_b_b, BN1);
-    if (rc) return rc;
-    p.splits = pick_splits(p, cdiv(N, BN1) * cdiv(M, BM), splitk_ws, ws_floats);
-    pick_staged(p);
-    const int batch = nh > 0 ? nh * nb : 0;
-    if (BN1 == 64) return launch1<64, 4>(ma, mb, p, batch, st);
-    return launch1<128, 3>(ma, mb, p, batch, st);
-  }
-  rc = make_map(&mb, B, N, K, ldb, 0, 0, 0, 0, bn / 2);
+  rc = make_map(&mb, B, N, K, ldb, nh, nb, stride_b_h, stride_b_b, c.bn / c.ctas);
   if (rc) return rc;
-  p.splits = pick_splits(p, 2 * cdiv(M, 2 * BM) * cdiv(N, bn), splitk_ws, ws_floats);
-  pick_staged(p);
-  return dispatch2(bn, ma, mb, p, st);
+  return dispatch(c, pick_mode(p, c), ma, mb, p, nh > 0 ? nh * nb : 0, st);
 }

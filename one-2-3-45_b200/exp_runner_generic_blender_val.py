@@ -4,8 +4,12 @@ Command-line mirror of the reference's reconstruction/exp_runner_generic_blender
 modes of the lod-0 demo configuration:
   export_mesh   <exp_dir>/{pose.json, stage1_8, stage2_8} -> <exp_dir>/mesh.ply   (what run.py's reconstruct() shells out to)
   val           volume-renders the query view -> <exp_dir>/val_color.png, val_depth.npy, val_normal.npy
-`--conf` is accepted for compatibility (the constants of confs/one2345_lod0_val_demo.conf are built in); training modes
-stay with the reference.  Without `--checkpoint_path` the seeded synthetic weights are used.
+`--conf` is parsed (o2345/checkpoints.py: the HOCON subset the reference's confs use; pyhocon is not needed) and supplies
+`model.sdf_network_lod0` (voxel_size, vol_dims, ...), `model.variance_network`, `model.rendering_network`, `model.trainer`
+(samples, perturb) and `general.base_exp_dir`; if the file does not exist the constants of
+confs/one2345_lod0_val_demo.conf are used.  Weights: `--checkpoint_path`, else -- as the reference does with
+`--is_continue` (:137-149) -- the lexicographically last `<base_exp_dir>/checkpoints/ckpt*.pth`, else the seeded synthetic
+weights.  Training modes stay with the reference.
 """
 import argparse
 import os
@@ -38,17 +42,27 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device: the o2345 path has no CPU fallback")
     from o2345 import synthetic as S
+    from o2345.checkpoints import latest_checkpoint, load_conf, recon_states
     from o2345.pipeline import build_networks, load_sample
     dev = torch.device("cuda", args.local_rank)
     torch.cuda.set_device(dev)
     exp_dir = args.specific_dataset_name
+    note = lambda m: print(m, file=sys.stderr)
+    conf = load_conf(args.conf) if os.path.exists(args.conf) else None
+    if conf is None:
+        note(f"conf {args.conf!r} not found: using the built-in constants of confs/one2345_lod0_val_demo.conf")
     states = S.all_states(0)
-    if args.checkpoint_path:
-        ck = torch.load(args.checkpoint_path, map_location="cpu")
-        states = {"pyramid_feature_network": ck.get("pyramid_feature_network", ck.get("pyramid_feature_network_lod0")),
-                  "sdf_network_lod0": ck["sdf_network_lod0"], "rendering_network_lod0": ck["rendering_network_lod0"],
-                  "variance_network_lod0": ck["variance_network_lod0"]}
-    trainer = build_networks(dev, vol_dim=96, states=states, perturb=0.0, base_exp_dir=exp_dir)
+    ckpt = args.checkpoint_path
+    if ckpt is None and conf is not None and args.is_continue:
+        ckpt = latest_checkpoint(conf['general.base_exp_dir'])
+        if ckpt is not None:
+            note(f"Find checkpoint: {os.path.basename(ckpt)}")
+    if ckpt is not None:
+        states.update(recon_states(torch.load(ckpt, map_location="cpu"), report=note))
+    else:
+        note("no checkpoint: seeded synthetic reconstruction weights")
+    trainer = build_networks(dev, states=states, base_exp_dir=exp_dir, conf=conf,
+                             **({} if conf is not None else {"vol_dim": 96, "perturb": 0.0}))
     sample = load_sample(exp_dir, dev)
     if args.mode == "export_mesh":
         mesh = trainer(sample, mode="export_mesh", resolution=args.resolution)

@@ -82,6 +82,8 @@ _SIGS = {
     "o2345_gemm_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int,
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
     "o2345_debug_gemm_trace": (None, [c_fp]),
+    "o2345_debug_gemm_force": (None, [C.c_int, C.c_int, C.c_int]),
+    "o2345_last_trap": (C.c_int, [C.c_char_p, C.c_size_t]),
     "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64,
                                     C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
     "o2345_groupnorm_scratch_floats": (c_i64, [C.c_int, C.c_int]),
@@ -111,7 +113,7 @@ _SIGS = {
 }
 
 EXPORTED = tuple(_SIGS)
-ABI_VERSION = 2          # include/o2345.h: O2345_ABI_VERSION
+ABI_VERSION = 3          # include/o2345.h: O2345_ABI_VERSION
 _lib = None
 
 
@@ -135,6 +137,12 @@ def load():
                              "rebuild with `python one-2-3-45_b200/build.py`")
         _lib = lib
     return _lib
+
+
+def last_trap() -> str:
+    """Description of the bounded GEMM wait that expired (and trapped) in this process, or '' if none did."""
+    buf = C.create_string_buffer(512)
+    return buf.value.decode(errors="replace") if load().o2345_last_trap(buf, 512) == 1 else ""
 
 
 def last_error() -> str:

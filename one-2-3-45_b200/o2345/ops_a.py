@@ -22,11 +22,12 @@ def _v(t):
 
 
 _WS = {}
-WS_FLOATS = 4 << 20   # 16 MB: covers M*N up to 2048 x 2048
+WS_FLOATS = (8 << 20) + 4096   # 32 MB of split-K partial planes (e.g. 4 planes of 2048 x 1024) + the 4096 ticket words at the end
 
 
 def _splitk_ws(dev):
-    """Zeroed fp32 workspace for split-K partial tiles (the finalize kernel leaves it zeroed again)."""
+    """fp32 workspace for split-K partial planes; zero-filled once because its last 4096 words are the tile tickets, which
+    the kernel expects (and leaves) zero."""
     k = str(dev)
     if k not in _WS:
         _WS[k] = torch.zeros(WS_FLOATS, dtype=_f32, device=dev)

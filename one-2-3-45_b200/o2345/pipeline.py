@@ -20,29 +20,32 @@ from .sparse_sdf_network import SparseSdfNetwork
 from .trainer_generic import GenericTrainer
 
 
-class Conf(dict):
-    """pyhocon-like view of the few conf entries the inference path reads."""
-
-    def get_int(self, key, default=None):
-        return int(self.get(key, default))
-
-    def get_float(self, key, default=None):
-        return float(self.get(key, default))
-
-    def get_bool(self, key, default=None):
-        return bool(self.get(key, default))
+from .checkpoints import Conf  # noqa: E402,F401
 
 
 def build_networks(device, vol_dim=96, states=None, n_samples=64, n_importance=64, perturb=1.0, base_exp_dir=None,
-                   variance_init=0.3):
-    """FeatureNet, SparseSdfNetwork, SingleVarianceNetwork, GeneralRenderingNetwork, GenericTrainer on `device`
-    with the constants of reference confs/one2345_lod0_val_demo.conf:66-129 (voxel_size = 2/(D-1))."""
+                   variance_init=0.3, conf=None):
+    """FeatureNet, SparseSdfNetwork, SingleVarianceNetwork, GeneralRenderingNetwork, GenericTrainer on `device`, assembled
+    like Runner.__init__ (reference exp_runner_generic_blender_val.py:93-132).  With `conf` (a parsed
+    confs/one2345_lod0_val_demo.conf) the constructor arguments come from it, exactly as the reference passes
+    `**conf['model.sdf_network_lod0']` etc. -- including its 8-digit voxel_size 0.02105263; without it the same
+    constants are built in (voxel_size = 2 / (D - 1) in full precision)."""
     fnet = FeatureNet()
-    sdf = SparseSdfNetwork(lod=0, ch_in=56, voxel_size=2.0 / (vol_dim - 1), vol_dims=[vol_dim] * 3, hidden_dim=128,
-                           cost_type='variance_mean', d_pyramid_feature_compress=16, regnet_d_out=16,
-                           num_sdf_layers=4, multires=6)
-    var = SingleVarianceNetwork(variance_init)
-    rnet = GeneralRenderingNetwork(in_geometry_feat_ch=16, in_rendering_feat_ch=56, anti_alias_pooling=True)
+    if conf is not None:
+        if conf.get_int('model.num_lods') != 1:
+            raise NotImplementedError("num_lods > 1 (the lod-1 refinement networks) is a 'next' row, SURVEY.md 8(f) item 3")
+        sdf = SparseSdfNetwork(**conf['model.sdf_network_lod0'])
+        var = SingleVarianceNetwork(**conf['model.variance_network'])
+        rnet = GeneralRenderingNetwork(**conf['model.rendering_network'])
+        tk = dict(conf['model.trainer'])
+    else:
+        sdf = SparseSdfNetwork(lod=0, ch_in=56, voxel_size=2.0 / (vol_dim - 1), vol_dims=[vol_dim] * 3, hidden_dim=128,
+                               cost_type='variance_mean', d_pyramid_feature_compress=16, regnet_d_out=16,
+                               num_sdf_layers=4, multires=6)
+        var = SingleVarianceNetwork(variance_init)
+        rnet = GeneralRenderingNetwork(in_geometry_feat_ch=16, in_rendering_feat_ch=56, anti_alias_pooling=True)
+        tk = dict(n_samples_lod0=n_samples, n_importance_lod0=n_importance, n_samples_lod1=64, n_importance_lod1=64,
+                  n_outside=0, perturb=perturb, alpha_type='div')
     if states is not None:
         load = lambda m, sd: m.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in sd.items()}, strict=False)
         for m, key in ((fnet, "pyramid_feature_network"), (sdf, "sdf_network_lod0"), (rnet, "rendering_network_lod0"),
@@ -54,9 +57,11 @@ def build_networks(device, vol_dim=96, states=None, n_samples=64, n_importance=6
         m.to(device)
         for p in m.parameters():
             p.requires_grad_(False)
-    conf = Conf({"general.base_exp_dir": base_exp_dir, "model.num_lods": 1})
-    trainer = GenericTrainer(None, fnet, None, sdf, None, var, None, rnet, None, n_samples, n_importance, 64, 64, 0,
-                             perturb, alpha_type='div', conf=conf, base_exp_dir=base_exp_dir)
+    if conf is None:
+        conf = Conf({"general": Conf({"base_exp_dir": base_exp_dir}), "model": Conf({"num_lods": 1})})
+    trainer = GenericTrainer(None, fnet, None, sdf, None, var, None, rnet, None, tk["n_samples_lod0"], tk["n_importance_lod0"],
+                             tk["n_samples_lod1"], tk["n_importance_lod1"], tk["n_outside"], tk["perturb"],
+                             alpha_type=tk["alpha_type"], conf=conf, base_exp_dir=base_exp_dir)
     return trainer
 
 

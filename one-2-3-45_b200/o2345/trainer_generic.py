@@ -17,24 +17,7 @@ from .featurenet import obtain_pyramid_feature_maps
 from .sparse_neus_renderer import SparseNeuSRenderer
 
 
-def write_ply(path, vertices, triangles, colors):
-    """Binary little-endian PLY with per-vertex RGBA, the layout trimesh emits for vertex colours."""
-    v = np.asarray(vertices, np.float32)
-    f = np.asarray(triangles, np.int32)
-    c = np.asarray(colors, np.uint8)
-    if c.shape[1] == 3:
-        c = np.concatenate([c, np.full((len(c), 1), 255, np.uint8)], 1)
-    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
-              "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\n"
-              "element face %d\nproperty list uchar int vertex_indices\nend_header\n") % (len(v), len(f))
-    vrec = np.empty(len(v), dtype=[("p", "<f4", 3), ("c", "u1", 4)])
-    vrec["p"], vrec["c"] = v, c
-    frec = np.empty(len(f), dtype=[("n", "u1"), ("i", "<i4", 3)])
-    frec["n"], frec["i"] = 3, f
-    with open(path, "wb") as fh:
-        fh.write(header.encode("ascii"))
-        fh.write(vrec.tobytes())
-        fh.write(frec.tobytes())
+from .mesh_io import merge_vertices, write_ply  # noqa: E402,F401  (write_ply re-exported: tests and tools import it from here)
 
 
 class GenericTrainer(nn.Module):
@@ -136,6 +119,7 @@ class GenericTrainer(nn.Module):
             density_or_sdf_network, bmin, bmax, resolution=resolution, threshold=threshold,
             device=conditional_volume.device, conditional_volume=conditional_volume, lod=lod,
             occupancy_mask=occupancy_mask)
+        vertices_unit = vertices
         vt = torch.tensor(vertices).to(conditional_volume)
         rgb, _ = self.sdf_renderer_lod0.blend_points(vt, density_or_sdf_network, rendering_network, conditional_volume,
                                                      conditional_valid_mask_volume, feature_maps, color_maps, w2cs,
@@ -148,6 +132,11 @@ class GenericTrainer(nn.Module):
             vh = np.concatenate([vertices, np.ones_like(vertices[:, :1])], axis=1)
             vertices = (vh @ tm.T)[:, :3]
         colors = (rgb.cpu() * 255).numpy().astype(np.uint8)
+        # trimesh.Trimesh(vertices, triangles, vertex_colors=...) with its default process=True merges coincident
+        # vertices before the export (reference :1374-1380)
+        lo, hi = np.asarray(bound_min, np.float64), np.asarray(bound_max, np.float64)
+        lattice = (vertices_unit - lo[None]) / (hi - lo)[None] * (resolution - 1.0)
+        vertices, triangles, colors = merge_vertices(vertices, triangles, colors, lattice_positions=lattice)
         if self.base_exp_dir is not None:
             os.makedirs(self.base_exp_dir, exist_ok=True)
             write_ply(os.path.join(self.base_exp_dir, 'mesh.ply'), vertices, triangles, colors)

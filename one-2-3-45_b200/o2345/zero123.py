@@ -185,6 +185,42 @@ def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=
     return stage1, stage2, pose
 
 
+def load_zero123_checkpoint(ckpt, device="cpu", use_ema=True, unet_config=None, first_stage_config=None, clip=True,
+                            report=print):
+    """LatentDiffusion from a Zero123 checkpoint (`zero123-xl.ckpt`: a Lightning file with a `state_dict`, or the state
+    dict itself), ready to sample the way the reference does (utils/zero123_utils.py:31-47, 60-98):
+      * the UNet weights are the EMA shadow `model_ema.*` (the reference samples inside `ema_scope()`);
+      * the CLIP ViT-L/14 image tower is attached and `cond_stage_model.*` loaded (text-side CLIP keys are ignored);
+      * anything the sampling path needs and the file lacks is an ERROR, not a silent default."""
+    from .checkpoints import zero123_sampling_state
+    sd = torch.load(ckpt, map_location="cpu") if isinstance(ckpt, (str, os.PathLike)) else ckpt
+    sd = sd.get("state_dict", sd)
+    m = LatentDiffusion(unet_config=unet_config, first_stage_config=first_stage_config)
+    if clip:
+        from .clip_image import FrozenCLIPImageEmbedder
+        m.cond_stage_model = FrozenCLIPImageEmbedder()
+    names = [n for n, _ in m.model.named_parameters()]
+    sd = zero123_sampling_state(sd, names, use_ema=use_ema, report=report)
+    res = m.load_state_dict(sd, strict=False)
+    needed = ("model.diffusion_model.", "first_stage_model.", "cc_projection.") + (("cond_stage_model.model.visual.",) if clip else ())
+    missing = [k for k in res.missing_keys if k.startswith(needed)]
+    if missing:
+        raise KeyError(f"checkpoint lacks {len(missing)} tensors the sampling path needs, e.g. {missing[:3]}")
+    ignored = [k for k in res.unexpected_keys if not k.startswith(("cond_stage_model.model.", "first_stage_model.loss", "model_ema."))
+               and k not in _SCHEDULE_KEYS]
+    if ignored and report is not None:
+        report(f"zero123 checkpoint: {len(ignored)} unused keys, e.g. {ignored[:3]}")
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m.to(device)
+
+
+# buffers of the reference's DDPM.register_schedule that the sampler does not read (ddpm.py:150-178)
+_SCHEDULE_KEYS = {"sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                  "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+                  "posterior_mean_coef2", "logvar"}
+
+
 def build_zero123(device, seed=0, clip=False):
     """LatentDiffusion with seeded random weights (no checkpoint exists offline).  clip=True attaches the CLIP ViT-L/14
     image tower (row A8, o2345/clip_image.py) as cond_stage_model instead of the fixed stand-in embedding."""

@@ -7,7 +7,10 @@ Command-line mirror of the reference's run.py:99-119 for the two accelerated pat
 Not built: SAM / rembg foreground extraction -- the input must already be a segmented object on a
 plain (or transparent) background -- and the LoFTR elevation search (`--polar_angle`, default 60).  Checkpoints: without
 `--zero123_ckpt` / `--recon_ckpt` the seeded synthetic weights of o2345.synthetic are used (there is no network access to
-fetch the released ones); with them, the reference's own files load through load_state_dict.
+fetch the released ones).  With `--zero123_ckpt` the file is loaded the way the reference samples from it: the UNet takes
+the EMA shadow (`model_ema.*`, reference ldm/modules/ema.py:14-21 + ddpm.py:180-193), the CLIP ViT-L/14 image tower is
+attached and takes `cond_stage_model.*`; a file that lacks what the sampler needs is refused.  `--output_format .obj/.glb`
+follow reference utils/utils.py:31-45 (o2345/mesh_io.py).
 """
 import argparse
 import os
@@ -36,7 +39,8 @@ def main(argv=None):
     ap.add_argument('--gpu_idx', type=int, default=0, help='GPU index')
     ap.add_argument('--half_precision', action='store_true', help='accepted for compatibility: the UNet / VAE kernels are fp16')
     ap.add_argument('--mesh_resolution', type=int, default=256, help='Mesh resolution')
-    ap.add_argument('--output_format', type=str, default=".ply", help='Output format: .ply (.obj / .glb need trimesh: not built)')
+    ap.add_argument('--output_format', type=str, default=".ply", help='Output format: .ply, .obj, .glb')
+    ap.add_argument('--no_ema', action='store_true', help='sample with model.* instead of the EMA shadow model_ema.* (the reference uses EMA)')
     ap.add_argument('--polar_angle', type=float, default=60.0, help='elevation of the input view in degrees (not estimated)')
     ap.add_argument('--zero123_ckpt', type=str, default=None, help='zero123-xl.ckpt (state_dict); default: seeded synthetic weights')
     ap.add_argument('--recon_ckpt', type=str, default=None, help='reconstruction checkpoint (ckpt_*.pth); default: seeded synthetic weights')
@@ -50,26 +54,19 @@ def main(argv=None):
     torch.cuda.set_device(dev)
 
     if args.zero123_ckpt:
-        sd = torch.load(args.zero123_ckpt, map_location="cpu")
-        sd = sd.get("state_dict", sd)
-        if any(k.startswith("cond_stage_model.") for k in sd):
-            print("note: the CLIP image tower (cond_stage_model.*) is not built; a fixed embedding stands in for it", file=sys.stderr)
-        model = LatentDiffusion()
-        res = model.load_state_dict({k: v for k, v in sd.items() if not k.startswith(("cond_stage_model.", "model_ema."))},
-                                    strict=False)
-        print(f"zero123 checkpoint: {len(res.missing_keys)} missing / {len(res.unexpected_keys)} unexpected keys", file=sys.stderr)
-        model = model.requires_grad_(False).to(dev)
+        from o2345.zero123 import load_zero123_checkpoint
+        model = load_zero123_checkpoint(args.zero123_ckpt, dev, use_ema=not args.no_ema,
+                                        report=lambda m: print(m, file=sys.stderr))
     else:
         print("no --zero123_ckpt: seeded synthetic Zero123 weights (the generated views are noise-like)", file=sys.stderr)
-        model = build_zero123(dev, seed=0)
+        model = build_zero123(dev, seed=0, clip=True)
     model = model.half()
 
     states = S.all_states(0)
     if args.recon_ckpt:
+        from o2345.checkpoints import recon_states
         ck = torch.load(args.recon_ckpt, map_location="cpu")
-        states = {"pyramid_feature_network": ck.get("pyramid_feature_network", ck.get("pyramid_feature_network_lod0")),
-                  "sdf_network_lod0": ck["sdf_network_lod0"], "rendering_network_lod0": ck["rendering_network_lod0"],
-                  "variance_network_lod0": ck["variance_network_lod0"]}
+        states.update(recon_states(ck, report=lambda m: print(m, file=sys.stderr)))
     shape_id = os.path.basename(args.img_path).split('.')[0]
     shape_dir = os.path.join("exp", shape_id)
     os.makedirs(shape_dir, exist_ok=True)
@@ -77,12 +74,17 @@ def main(argv=None):
 
     mesh = image_to_mesh(model, trainer, load_input(args.img_path), polar_angle=args.polar_angle,
                          resolution=args.mesh_resolution, exp_dir=shape_dir)
-    ply = os.path.join(shape_dir, "mesh.ply")
-    if args.output_format != ".ply":
-        print("Invalid output format for this build (only .ply is written)", file=sys.stderr)
+    mesh_path = os.path.join(shape_dir, "mesh.ply")
+    if args.output_format == ".ply":          # reference run.py:113-118
+        pass
+    elif args.output_format not in (".obj", ".glb"):
+        print("Invalid output format, must be one of .ply, .obj, .glb")
+    else:
+        from o2345.mesh_io import convert_mesh_format
+        mesh_path = convert_mesh_format(shape_dir, args.output_format)
     print(f"{len(mesh['vertices'])} vertices, {len(mesh['triangles'])} triangles")
-    print("Mesh saved to:", ply)
-    return ply
+    print("Mesh saved to:", mesh_path)
+    return mesh_path
 
 
 if __name__ == "__main__":

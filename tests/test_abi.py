@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/o2345.h but not exported"
-    assert lib.o2345_abi_version() == 2
+    assert lib.o2345_abi_version() == _lib.ABI_VERSION
 
 
 def test_ctypes_table_matches_header():
