@@ -33,7 +33,7 @@ extern "C" {
 #define O2345_EUNSUPPORTED (-3)
 
 #define O2345_ABI_VERSION 3   /* 2: o2345_epilogue, precision arguments of sdf_query / render_blend, GroupNorm as affine
-                                 3: split-K tickets inside the workspace (no finalize kernel), o2345_last_trap, o2345_debug_gemm_force */
+                                 3: split-K inside the GEMM kernel (cluster per tile, private planes in the workspace), o2345_last_trap, o2345_debug_gemm_force */
 
 typedef void* o2345_stream_t;
 
@@ -279,17 +279,22 @@ typedef struct {
                             32 = 16 values followed by their 16 gates, C gets N/2 columns value * gelu(gate) */
   float alpha;           /* scale on the accumulator */
   int out_f32;           /* C is fp32 instead of fp16 */
+  float* colstats;       /* optional fp32 [M / stats_rows_per_group, 2, N], zero on entry: the kernel ADDS, per row group (image)
+                            and column, the sum and the sum of squares of the fp16 values it writes -- the statistics the next
+                            GroupNorm needs (openaimodel.py:256-276), so that no kernel has to re-read the tensor for them.
+                            fp16 output, act 0, N and ldc multiples of 8; stats_rows_per_group 64 or a multiple of 128 */
+  int stats_rows_per_group;
 } o2345_epilogue;
 
 int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
                    int64_t ldc, int nh, int nb, int64_t stride_a_h, int64_t stride_a_b, int64_t stride_b_h,
                    int64_t stride_b_b, int64_t stride_c_h, int64_t stride_c_b, const o2345_epilogue* ep /* NULL: plain */,
                    float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
-/* splitk_ws (optional, may be NULL): fp32 scratch of ws_floats elements.  Its last 4096 words hold per-tile tickets and must
- * be ZERO on entry (they are left zero); the rest holds up to floor((ws_floats - 4096) / (M*N)) private partial planes and
- * needs no initialisation.  When the output tiles alone cannot fill the GPU the K range is split over several CTAs per
- * tile; each stores its partial tile in its own plane and the last CTA of a tile to arrive sums the planes and applies the
- * epilogue.  One workspace serves one stream at a time. */
+/* splitk_ws (optional, may be NULL): fp32 scratch of ws_floats elements, no initialisation needed.  When the output tiles
+ * alone cannot fill the GPU the K range is split over up to min(8, ws_floats / (M*N)) CTA pairs per tile that run as one
+ * thread-block cluster: each stores its partial tile in its own [M, N] plane of the scratch, a cluster barrier publishes the
+ * planes, and every split sums them and applies the epilogue to its share of the tile.  One workspace serves one stream at
+ * a time. */
 
 /* Every mbarrier wait inside the GEMM kernel is bounded (4 s).  If one expires the kernel records which barrier of which CTA
  * of which problem stalled in a host-mapped buffer and traps (the CUDA context then reports a launch failure at the next
@@ -300,6 +305,9 @@ int o2345_last_trap(char* buf, size_t n);
 /* Tuning hook (tools/gemm_sweep.py; not part of the data path): force the tile configuration of the following non-batched
  * GEMM / conv calls: ctas in {1, 2}, bn in {64, 128, 160, 256}, splits >= 1; 0 keeps the heuristic's choice of that field. */
 void o2345_debug_gemm_force(int ctas, int bn, int splits);
+/* Tuning hook: the seven constants of the tile-configuration cost model (per-SM ingest B/clk, two-CTA bonus, fabric B/clk,
+ * fixed us, epilogue us per 160 columns, split-K us, split-K us per split and 128 columns); see gemm_tc.cu predict_us. */
+void o2345_debug_gemm_model(const float* seven);
 
 /* Diagnostic hook (not part of the data path): when device_buf16 != NULL, CTA (0,0,0) of every following CTA-pair GEMM
  * launch stores clock64() stamps of its phases into device_buf16[0..8] (entry, prologue done, first TMA issued, last TMA
@@ -330,6 +338,13 @@ int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps,
  * pad_lo on the low side (pad_lo < 0: k/2; pad_lo = 0 reproduces the VAE encoder's F.pad(x, (0,1,0,1))). */
 int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample, int pad_lo,
                           const float* scale, const float* shift, int act, void* out, o2345_stream_t stream);
+/* The same gather with GroupNorm(x) (+SiLU if act) computed from RAW statistics: stats_a [B, 2, Ca] (sum, then sum of squares,
+ * per image and channel, over the H*W pixels of x) for channels [0, Ca) and stats_b [B, 2, C - Ca] for the rest (NULL when
+ * Ca == C) -- the tables the producing GEMMs accumulated through o2345_epilogue.colstats (two tables: x is a channel
+ * concat).  G groups, eps, gamma / beta [C] (may be NULL).  Replaces o2345_groupnorm_stats + o2345_norm_act_im2col. */
+int o2345_norm_act_im2col_stats(const void* x, int B, int H, int W, int C, int ksize, int stride, int upsample, int pad_lo,
+                                const float* stats_a, int Ca, const float* stats_b, int G, float eps, const float* gamma,
+                                const float* beta, int act, void* out, o2345_stream_t stream);
 int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,
                          o2345_stream_t stream);
 int o2345_softmax_rows(const void* s, int64_t rows, int n, void* p, o2345_stream_t stream);

@@ -72,10 +72,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-// Same, for kernels that run as thread-block clusters of `cluster_x` CTAs along x (1: no cluster attribute).
+// Same, for kernels that run as thread-block clusters of (cluster_x, 1, cluster_z) CTAs ((1, 1, 1): no cluster attribute).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
-                                      Args... args) {
+                                      int cluster_z, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
@@ -83,9 +83,9 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   int n = 1;
-  if (cluster_x > 1) {
+  if (cluster_x > 1 || cluster_z > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = cluster_x, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+    attr[n].val.clusterDim.x = cluster_x, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = cluster_z;
     ++n;
   }
   cfg.attrs = attr, cfg.numAttrs = n;

@@ -24,9 +24,13 @@
 // MODE selects the epilogue at compile time (round 1 inlined every variant into one 9 600-instruction body):
 //   0 staged, no activation   1 staged, GEGLU gate   2 staged, SiLU / GELU / QuickGELU (runtime switch per tile)
 //   3 generic (fp32 output, batched, unaligned N) and SPLIT-K.
-// Split-K (tiles alone cannot fill 148 SMs): each of the `splits` CTAs of a tile stores its partial accumulator into its own
-// fp32 plane of the workspace and takes a ticket; the LAST one to arrive sums the planes, applies the epilogue and zeroes the
-// ticket (round 1 added into one plane with L2 atomics and launched a second kernel: 92 extra launches per UNet iteration).
+// Split-K (tiles alone cannot fill 148 SMs): the `splits` CTAs (pairs) of a tile are launched as ONE thread-block cluster
+// (CTAS, 1, splits), so the hardware co-schedules them.  Each stores its partial accumulator into its own fp32 plane of the
+// workspace, a cluster barrier (release / acquire) publishes the planes, and every split then sums the planes and applies
+// the epilogue to ITS share of the tile.  No atomics, no tickets, no zero-initialised scratch, no second kernel (round 1
+// added into one plane with L2 atomics -- they sustain only ~90 G elements/s -- and launched a finalize kernel: 92 extra
+// launches per UNet iteration; a first round-2 version let the last-arriving CTA finish the tile alone: 13-19 us of
+// serial L2 round trips, see profiles/r2_gemm_trace.txt).
 // Every mbarrier wait is bounded in TIME (4 s): a protocol bug or a lost arrival records which barrier of which CTA of
 // which problem stalled in a host-visible buffer (o2345_last_trap) and traps, instead of spinning for tens of minutes.
 #include <cuda.h>
@@ -44,7 +48,7 @@ constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr uint64_t WAIT_LIMIT_NS = 4000000000ull;   // bounded waits: a protocol bug traps (with a record) instead of hanging the GPU
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;         // clears the CTA-rank bit of a shared::cluster address: "the even CTA of my pair"
-constexpr int TICKET_INTS = 4096;                   // split-K tickets live in the last TICKET_INTS words of the workspace
+constexpr int MAX_CLUSTER = 16;                     // CTAS * splits: one cluster per tile (non-portable size, opted into per kernel)
 constexpr int RES_PREFETCH = 8;                     // 16-byte residual pieces per lane fetched before the accumulator is ready
 
 enum { WAIT_EMPTY = 1, WAIT_FULL = 2, WAIT_ACC = 3 };   // which wait timed out (o2345_last_trap)
@@ -144,15 +148,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// pair: arrives on the barrier at this shared-memory offset in BOTH CTAs once the pair's MMAs so far have finished
+// pair: arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair (cluster ranks 2j and 2j + 1: `mask`)
+// once the pair's MMAs so far have finished
 template <int CTAS>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t mask) {
   if (CTAS == 2)
-    asm volatile(
-        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
-        ::"r"(smem_u32(bar))
-        : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
   else
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -189,13 +192,12 @@ struct GemmParams {
   // 4-D tensor map (C, W, H, B); an output tile of 128 consecutive pixels is a box (64 ch, tw, th, tb), and kernel tap
   // (ky, kx) is the same box shifted by (kx-1, ky-1) -- TMA's out-of-bounds zero fill IS the convolution padding.
   int conv, cC, cH, cW, cblocks;
-  // split-K: CTA z of a tile stores its partial accumulator in plane z of ws [splits, M, N]; the last CTA of a tile to take
-  // its ticket sums the planes and applies the epilogue (tickets: zero on entry, left zero).
+  // split-K: the splits of a tile form one cluster; CTA z stores its partial accumulator in plane z of ws [splits, M, N],
+  // the cluster barrier publishes the planes, then every split sums and finishes its share of the tile.
   int splits;
   float* ws;
-  int* tickets;
-  // GroupNorm statistics of the OUTPUT (staged modes): colstats[g * N + col] += x and colstats[(groups + g) * N + col] += x^2
-  // of the final fp16 values of row group g = row / stats_rpg (the consumer turns them into mean / rstd); nullptr: off
+  // GroupNorm statistics of the OUTPUT: colstats[(g * 2 + 0) * N + col] += x and colstats[(g * 2 + 1) * N + col] += x^2 over the
+  // final fp16 values of row group g = row / stats_rpg (the consumer turns them into mean / rstd); nullptr: off
   float* colstats;
   int stats_rpg, stats_groups;
   long long* trace;            // diagnostic: CTA (0,0,0) stores clock64() stamps of its phases (o2345_debug_gemm_trace), else nullptr
@@ -205,6 +207,10 @@ struct GemmParams {
 
 __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
   if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = clock64();
+}
+// wall-clock (globaltimer, ns) stamps of tile (0,0): comparable across the SMs the splits of a tile run on
+__device__ __forceinline__ void stamp_ns(const GemmParams& p, int slot, bool any_z = false) {
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (any_z || blockIdx.z == 0)) p.trace[slot] = (long long)global_ns();
 }
 
 __device__ __noinline__ void wait_timed_out(const GemmParams& p, int tag, int stage) {
@@ -326,82 +332,105 @@ __device__ __forceinline__ void splitk_partial(const GemmParams& p, const uint32
   }
 }
 
-// split-K, the LAST CTA of a tile to take its ticket: out = act(alpha * sum_s ws[s] + bias + rowbias) + residual over the
-// CTA's 128 x BN block.  te = 0..255 (the epilogue threads): one thread per (row, 8 columns) when N and ldc allow 16-byte
-// accesses, else one per element.  The partials were written by other SMs: reads bypass L1; two pieces x two splits are in
-// flight per thread (8 x 16 bytes), enough to cover the L2 round trip at the SM's ingest rate.
+// split-K, after the cluster barrier: split z of a tile applies out = act(alpha * sum_s ws[s] + bias + rowbias) + residual to ITS
+// share (pieces [z, z + 1) * NP / splits) of the CTA's 128 x BN block.  te = 0..255 (the epilogue threads): one thread per
+// (row, 8 columns) when N and ldc allow 16-byte accesses, else one per element.  The planes were written by other SMs: reads
+// bypass L1.  Row-bias / residual loads are issued before the plane sums so that one round trip covers them all.
 template <int BN>
-__device__ __forceinline__ void splitk_finalize(const GemmParams& p, int m0, int n0, int te) {
+__device__ __forceinline__ void splitk_finalize(const GemmParams& p, int m0, int n0, int z, int te, float* sstat) {
   const bool vec = (p.N % 8) == 0 && (p.ldc % 8) == 0 && (!p.rowbias || (p.rowbias_ld % 8) == 0);
   const int64_t plane = (int64_t)p.M * p.N;
+  // GroupNorm statistics (fp16 output only; the host refuses other combinations): this split's rows fall into at most
+  // two row groups (stats_rpg is a multiple of 128, or 64): shared-memory accumulators [2 groups][2 moments][BN], then one
+  // red.add per column, moment and group for the whole share.
+  const bool stats = p.colstats != nullptr && vec && !p.out_f32;
+  if (stats) {
+    for (int i = te; i < 4 * BN; i += EPI_THREADS) sstat[i] = 0.f;
+    epi_bar();
+  }
   if (vec) {
     constexpr int PPR = BN / 8;
     constexpr int NP = BM * PPR;
-    for (int i = te; i < NP; i += 2 * EPI_THREADS) {
-      float v[2][8];
-      int64_t woff[2];
-      bool ok[2];
-      int rowq[2], colq[2];
+    const int share = (NP + p.splits - 1) / p.splits;
+    const int i1 = min(NP, (z + 1) * share);
+    // a thread's pieces are EPI_THREADS apart: when that is a multiple of the pieces per row its columns never change and
+    // the bias is fetched once
+    constexpr bool FIXED_COLS = (EPI_THREADS % PPR) == 0;
+    float bcol[8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int ii = i + u * EPI_THREADS;
-        const int rl = ii / PPR;
-        rowq[u] = m0 + rl, colq[u] = n0 + (ii - rl * PPR) * 8;
-        ok[u] = ii < NP && rowq[u] < p.M && colq[u] < p.N;
-        woff[u] = (int64_t)rowq[u] * p.N + colq[u];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+    for (int e = 0; e < 8; ++e) bcol[e] = 0.f;
+    if (FIXED_COLS && p.bias) {
+      const int i0 = z * share + te, col = n0 + (i0 - (i0 / PPR) * PPR) * 8;
+      if (col < p.N) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+        bcol[0] = b0.x, bcol[1] = b0.y, bcol[2] = b0.z, bcol[3] = b0.w, bcol[4] = b1.x, bcol[5] = b1.y, bcol[6] = b1.z, bcol[7] = b1.w;
       }
-      for (int s = 0; s < p.splits; s += 2) {
-        float4 a[2][2], b[2][2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const bool on = ok[u] && s + t < p.splits;
-            const float4* w = reinterpret_cast<const float4*>(p.ws + (int64_t)(s + t) * plane + woff[u]);
-            a[u][t] = on ? __ldcg(w) : make_float4(0.f, 0.f, 0.f, 0.f);
-            b[u][t] = on ? __ldcg(w + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            v[u][0] += a[u][t].x, v[u][1] += a[u][t].y, v[u][2] += a[u][t].z, v[u][3] += a[u][t].w;
-            v[u][4] += b[u][t].x, v[u][5] += b[u][t].y, v[u][6] += b[u][t].z, v[u][7] += b[u][t].w;
-          }
+    }
+    for (int i = z * share + te; i < i1; i += EPI_THREADS) {
+      const int rl = i / PPR, row = m0 + rl, col = n0 + (i - rl * PPR) * 8;
+      if (row >= p.M || col >= p.N) continue;
+      const int64_t woff = (int64_t)row * p.N + col, o = (int64_t)row * p.ldc + col;
+      uint4 qb = make_uint4(0u, 0u, 0u, 0u), qr = make_uint4(0u, 0u, 0u, 0u);
+      if (p.rowbias) qb = *reinterpret_cast<const uint4*>(p.rowbias + (int64_t)(row / p.rows_per_group) * p.rowbias_ld + col);
+      if (p.residual) qr = *reinterpret_cast<const uint4*>(p.residual + o);
+      if (!FIXED_COLS && p.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+        bcol[0] = b0.x, bcol[1] = b0.y, bcol[2] = b0.z, bcol[3] = b0.w, bcol[4] = b1.x, bcol[5] = b1.y, bcol[6] = b1.z, bcol[7] = b1.w;
       }
+      float v[8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (!ok[u]) continue;
-        const int row = rowq[u], col = colq[u];
-        const int64_t o = (int64_t)row * p.ldc + col;
-        if (p.rowbias) {
-          uint4 q = *reinterpret_cast<const uint4*>(p.rowbias + (int64_t)(row / p.rows_per_group) * p.rowbias_ld + col);
-          const __half* h = reinterpret_cast<const __half*>(&q);
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      for (int s = 0; s < p.splits; s += 4) {
+        float4 a[4], b[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[u][e] = fmaf(v[u][e], p.alpha, __half2float(h[e]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[u][e] *= p.alpha;
+        for (int t = 0; t < 4; ++t) {
+          const bool on = s + t < p.splits;
+          const float4* w = reinterpret_cast<const float4*>(p.ws + (int64_t)(s + t) * plane + woff);
+          a[t] = on ? __ldcg(w) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[t] = on ? __ldcg(w + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          v[0] += a[t].x, v[1] += a[t].y, v[2] += a[t].z, v[3] += a[t].w;
+          v[4] += b[t].x, v[5] += b[t].y, v[6] += b[t].z, v[7] += b[t].w;
+        }
+      }
+      const __half* hb = reinterpret_cast<const __half*>(&qb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = fmaf(v[e], p.alpha, p.rowbias ? __half2float(hb[e]) : 0.f) + bcol[e];
+        v[e] = apply_act(x, p.act);
+      }
+      if (p.residual) {
+        const __half* h = reinterpret_cast<const __half*>(&qr);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += __half2float(h[e]);
+      }
+      store8(p, o, v);
+      if (stats) {
+        float* acc = sstat + (row / p.stats_rpg - m0 / p.stats_rpg) * 2 * BN + (col - n0);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          if (p.bias) v[u][e] += __ldg(p.bias + col + e);
-          v[u][e] = apply_act(v[u][e], p.act);
+          const float x = __half2float(__float2half_rn(v[e]));       // the value the consumer will read back
+          atomicAdd(acc + e, x), atomicAdd(acc + BN + e, x * x);
         }
-        if (p.residual) {
-          uint4 q = *reinterpret_cast<const uint4*>(p.residual + o);
-          const __half* h = reinterpret_cast<const __half*>(&q);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[u][e] += __half2float(h[e]);
-        }
-        store8(p, o, v[u]);
+      }
+    }
+    if (stats) {
+      epi_bar();
+      const int g0 = m0 / p.stats_rpg;
+      const int last_row = m0 + BM - 1 < p.M ? m0 + BM - 1 : p.M - 1;
+      const int ng = last_row / p.stats_rpg - g0 + 1;                 // 1 or 2
+      for (int i = te; i < ng * 2 * BN; i += EPI_THREADS) {
+        const int gi = i / (2 * BN), rem = i - gi * 2 * BN, mom = rem / BN, c = rem - mom * BN;
+        if (n0 + c < p.N && sstat[i] != 0.f) atomicAdd(p.colstats + ((int64_t)(g0 + gi) * 2 + mom) * p.N + n0 + c, sstat[i]);
       }
     }
     return;
   }
-  for (int i = te; i < BM * BN; i += EPI_THREADS) {
+  const int share = (BM * BN + p.splits - 1) / p.splits;
+  const int i1 = min(BM * BN, (z + 1) * share);
+  for (int i = z * share + te; i < i1; i += EPI_THREADS) {
     const int rl = i / BN, row = m0 + rl, col = n0 + (i - rl * BN);
     if (row >= p.M || col >= p.N) continue;
     float x = 0.f;
@@ -581,7 +610,10 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const WarpO
       const int grow = row0 + rl, col = g.ocol0 + ci * 8;
       if (grow < p.M && col < g.nout) {
         uint4 v = *reinterpret_cast<const uint4*>(slab + rl * g.stride + ci * 16);
-        if (p.residual) v = add_h8(v, resq[u]);
+        if (p.residual) {
+          v = add_h8(v, resq[u]);
+          if (p.colstats) *reinterpret_cast<uint4*>(slab + rl * g.stride + ci * 16) = v;   // the statistics see the final value
+        }
         *reinterpret_cast<uint4*>(C + (int64_t)grow * p.ldc + col) = v;
       }
     }
@@ -606,8 +638,44 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const WarpO
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       if (!ok[u]) continue;
-      if (p.residual) v[u] = add_h8(v[u], q[u]);
+      if (p.residual) {
+        v[u] = add_h8(v[u], q[u]);
+        if (p.colstats) {
+          const int pp = base + 32 * u;
+          const int rl = pp / g.ppr, ci = pp - rl * g.ppr;
+          *reinterpret_cast<uint4*>(slab + rl * g.stride + ci * 16) = v[u];
+        }
+      }
       *reinterpret_cast<uint4*>(C + o[u]) = v[u];
+    }
+  }
+  // GroupNorm statistics of the tensor just written (the consumer's GroupNorm needs sum and sum of squares per image and
+  // channel group): column sums over this warp's 32 rows -- all in one image, stats_rpg is a multiple of 32 -- read back
+  // from the slab (lanes walk columns, conflict-free), one red.add per column and moment.
+  if (MODE == 0 && p.colstats) {
+    __syncwarp();
+    const int nrows = p.M - row0 < 32 ? p.M - row0 : 32;
+    if (nrows > 0) {
+      float* ssum = p.colstats + (int64_t)(row0 / p.stats_rpg) * 2 * g.nout;
+      for (int cp = lane; 2 * cp < g.outc; cp += 32) {
+        const int col = g.ocol0 + 2 * cp;
+        if (col >= g.nout) break;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (nrows == 32) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(slab + r * g.stride + cp * 4));
+            s0 += f.x, s1 += f.y, q0 = fmaf(f.x, f.x, q0), q1 = fmaf(f.y, f.y, q1);
+          }
+        } else {
+          for (int r = 0; r < nrows; ++r) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(slab + r * g.stride + cp * 4));
+            s0 += f.x, s1 += f.y, q0 = fmaf(f.x, f.x, q0), q1 = fmaf(f.y, f.y, q1);
+          }
+        }
+        atomicAdd(ssum + col, s0), atomicAdd(ssum + col + 1, s1);
+        atomicAdd(ssum + g.nout + col, q0), atomicAdd(ssum + g.nout + col + 1, q1);
+      }
     }
   }
 }
@@ -642,8 +710,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __half* srb = reinterpret_cast<__half*>(sbias + BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) stamp(p, 0);
-  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs, owns the full barriers)
+  if (threadIdx.x == 0) stamp(p, 0), stamp_ns(p, 16);
+  // cluster = (CTAS, 1, splits): ranks 2j and 2j + 1 are the pair of split j.  rank 0 = leader of its pair (issues the MMAs,
+  // owns the full barriers)
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = CTAS == 2 ? (crank & 1u) : 0u;
+  const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1u));
   const int m0 = CTAS == 2 ? (blockIdx.x >> 1) * (2 * BM) + (int)rank * BM : blockIdx.x * BM;
   const int n0 = blockIdx.y * BN, bz = blockIdx.z;
   const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
@@ -732,9 +804,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)   // advancing 16 fp16 along K inside the 128-byte swizzle atom = +32 bytes on the start address
           umma_f16<CTAS>(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, ((kb - kb0) | k) != 0);
-        umma_commit<CTAS>(empty + s);   // frees this stage (pair: in both CTAs) once these MMAs have read it
+        umma_commit<CTAS>(empty + s, pair_mask);   // frees this stage (pair: in both CTAs) once these MMAs have read it
       }
-      umma_commit<CTAS>(tmem_full);     // accumulator complete: the epilogue warps (pair: of both CTAs) may start
+      umma_commit<CTAS>(tmem_full, pair_mask);     // accumulator complete: the epilogue warps (pair: of both CTAs) may start
       stamp(p, 5);
     }
   } else {  // ------------------------ epilogue warps 2..9 on this CTA's 128 accumulator rows
@@ -758,25 +830,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = row0 + lane;
       if (p.splits > 1) {
+        if (te == 0) stamp_ns(p, 17);
 #pragma unroll 1
         for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem_row_base + c0, r);
           if (row < p.M) splitk_partial(p, r, bz, row, n0 + c0);
         }
-        __threadfence();                 // this thread's partial sums are visible before the CTA takes its ticket
-        epi_bar();
-        if (te == 0) {
-          int* tk = p.tickets + (blockIdx.y * gridDim.x + blockIdx.x);
-          const int last = atomicAdd(tk, 1) == p.splits - 1;
-          if (last) atomicExch(tk, 0);   // left zeroed for the next launch
-          tmem_slot[1] = (uint32_t)last;
-        }
-        epi_bar();
-        if (tmem_slot[1]) {
-          __threadfence();
-          splitk_finalize<BN>(p, m0, n0, te);
-        }
+        if (te == 0) stamp_ns(p, 18);
       } else {
         const int64_t crow = (p.batched ? (int64_t)(bz % p.nh) * p.stride_c_h + (int64_t)(bz / p.nh) * p.stride_c_b : 0) +
                              (int64_t)row * p.ldc;
@@ -791,13 +852,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 64) stamp(p, 7);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  // pair: neither CTA may free TMEM / exit while the pair's MMAs or the peer's TMEM reads are in flight
-  if (CTAS == 2) cluster_sync_all();
+  // pair: neither CTA may free TMEM / exit while the pair's MMAs or the peer's TMEM reads are in flight.
+  // split-K: the `splits` CTAs (pairs) of a tile form ONE cluster (co-scheduled by the hardware), so this barrier -- release /
+  // acquire at cluster scope -- also publishes every split's partial plane to its siblings.
+  const bool split = MODE == 3 && p.splits > 1;
+  if (CTAS == 2 || split) cluster_sync_all();
   else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+  }
+  if (MODE == 3) {
+    if (split && warp >= 2) {   // every split finalizes its share of the 128 x BN block: sum of the planes + epilogue
+      if (threadIdx.x == 64) stamp_ns(p, 21, true);
+      splitk_finalize<BN>(p, m0, n0, bz, threadIdx.x - 64, reinterpret_cast<float*>(smem));
+      if (threadIdx.x == 64) stamp_ns(p, 22, true);
+    }
   }
   if (threadIdx.x == 0) stamp(p, 8);
 }
@@ -871,19 +942,38 @@ void read_force_env() {
   if (e) sscanf(e, "%d,%d,%d", &g_force[0], &g_force[1], &g_force[2]);
 }
 
-int min_kblocks_per_split() {
-  static int v = -1;
-  if (v < 0) {   // k-blocks each split must keep (tuning knob)
-    const char* e = getenv("O2345_SPLITK_MIN_KB");
-    v = e ? atoi(e) : 8;
-    if (v < 1) v = 1;
-  }
-  return v;
+// Tile shape and k-splits for a problem of M x N with nk k-blocks of 64: the candidate with the lowest predicted time under a
+// small cost model fitted to tools/gemm_sweep.py (63 UNet shapes x ~40 forced configurations each on a B200, cold L2;
+// profiles/r2_gemm_sweep.txt: the model's picks total 3.23 ms against 3.18 ms for the per-shape optimum):
+//   * a launch costs ~5 us of fixed latency (launch, prologue, first TMA round trip, tear-down) + ~3 us of epilogue per
+//     160 columns of tile and wave of 296 CTAs;
+//   * the main loop is bound by operand delivery, not by the tensor pipe: an SM ingests ~40 B/clk (60 when two CTAs share it
+//     and cover each other's bubbles), the whole L2 -> SM fabric ~6 300 B/clk -- so few fat tiles starve (few SMs pull),
+//     many thin tiles re-read A (fabric), and long-K problems with few tiles want split-K;
+//   * split-K adds ~4 us + ~1 us per split and 128 tile columns (partial planes through L2, cluster barrier, finalize).
+float g_model[7] = {40.f, 0.5f, 6300.f, 5.f, 3.f, 4.f, 1.f};   // bw_sm, alpha, cap, fixed, epi, so0, so1 (tools: o2345_debug_gemm_model)
+float predict_us(int M, int N, int nk, int ctas, int bn, int splits) {
+  const float bw_sm = g_model[0], alpha = g_model[1], cap = g_model[2], fixed = g_model[3], epi = g_model[4], so0 = g_model[5],
+              so1 = g_model[6], cyc_per_us = 1900.f;
+  const int mblocks = ctas == 2 ? 2 * cdiv(M, 2 * BM) : cdiv(M, BM);
+  const int tiles = mblocks * cdiv(N, bn);
+  const int n = tiles * splits;
+  const int kb = cdiv(nk, splits);
+  const float bytes_cta = (float)kb * (float)(BM * BK * 2 + (bn / ctas) * BK * 2);
+  const int sms = sm_count();
+  const int rounds = cdiv(n, sms);
+  float f = (float)(n - sms) / (float)sms;
+  f = f < 0.f ? 0.f : (f > 1.f ? 1.f : f);
+  const float t_sm = (float)rounds * bytes_cta / (bw_sm * (1.f + alpha * f));
+  const float t_fabric = (float)n * bytes_cta / cap;
+  const float t_mma = (float)rounds * (float)kb * 4.f * ((float)bn * 0.5f);
+  float t = t_sm > t_fabric ? t_sm : t_fabric;
+  if (t_mma > t) t = t_mma;
+  float us = fixed + t / cyc_per_us + epi * (float)bn / 160.f * (float)cdiv(n, 2 * sms);
+  if (splits > 1) us += so0 + so1 * (float)splits * (float)bn / 128.f;
+  return us;
 }
 
-// Tile shape and k-splits for a problem of M x N with nk k-blocks of 64.  The resource to fill is 148 SMs x 2 resident
-// CTAs; per-tile fixed cost (prologue, first TMA round trip, epilogue, tear-down) is ~4 us, so small problems want many
-// small tiles and long-K problems with few tiles want split-K; large problems want the widest tile (operand traffic).
 Config pick_config(const GemmParams& p, int nk, bool can_split, int64_t ws_floats) {
   read_force_env();
   Config c;
@@ -892,35 +982,33 @@ Config pick_config(const GemmParams& p, int nk, bool can_split, int64_t ws_float
     c.ctas = 1, c.bn = N <= 64 ? 64 : 128, c.splits = 1;
     return c;
   }
-  c.ctas = M <= BM ? 1 : 2;
-  if (c.ctas == 1) {
-    c.bn = N <= 64 ? 64 : 128;
-  } else {
-    if (N <= 64) c.bn = 64;
-    else if (N % 160 == 0) c.bn = 160;
-    else if (N <= 128) c.bn = 128;
-    else c.bn = (N % 256 == 0 || N > 640) ? 256 : (N % 128 == 0 ? 128 : 160);
-    // few tiles and a short K: halve the tile width so that more SMs share the (latency-bound) work
-    const int tiles = 2 * cdiv(M, 2 * BM) * cdiv(N, c.bn);
-    if (tiles < sm_count() / 2 && nk <= 24 && c.bn > 64 && N % 64 == 0) c.bn = 64;
-  }
-  if (g_force[0] == 1 || g_force[0] == 2) c.ctas = g_force[0];
-  if (g_force[1] == 64 || g_force[1] == 128 || (c.ctas == 2 && (g_force[1] == 160 || g_force[1] == 256))) c.bn = g_force[1];
-  if (c.ctas == 1 && c.bn > 128) c.bn = 128;
-  const int mblocks = c.ctas == 2 ? 2 * cdiv(M, 2 * BM) : cdiv(M, BM);
-  const int ctas_total = mblocks * cdiv(N, c.bn);
-  c.splits = 1;
-  if (can_split && p.act != 3 && p.ws && 2 * (int64_t)M * N <= ws_floats - TICKET_INTS && ctas_total <= TICKET_INTS) {
-    const int max_planes = (int)((ws_floats - TICKET_INTS) / ((int64_t)M * N));
-    const int min_kb = min_kblocks_per_split();
-    if (ctas_total < 120 && nk >= 2 * min_kb) {
-      int s = 2 * sm_count() / ctas_total;
-      if (s > nk / min_kb) s = nk / min_kb;
-      if (s > 32) s = 32;
-      c.splits = s < 2 ? 1 : s;
+  static const int kBn[4] = {64, 128, 160, 256};
+  static const int kSplits[8] = {1, 2, 3, 4, 6, 8, 12, 16};
+  const bool split_ok = can_split && p.act != 3 && p.ws && 2 * (int64_t)M * N <= ws_floats;
+  const int max_planes = split_ok ? (int)(ws_floats / ((int64_t)M * N)) : 1;
+  float best = 1e30f;
+  c.ctas = 2, c.bn = 128, c.splits = 1;
+  for (int ctas = 1; ctas <= 2; ++ctas) {
+    if (ctas == 1 && M > 2 * BM) continue;                      // single-CTA tiles only pay for short problems
+    if ((g_force[0] == 1 || g_force[0] == 2) && ctas != g_force[0]) continue;
+    for (int bi = 0; bi < 4; ++bi) {
+      const int bn = kBn[bi];
+      if (ctas == 1 && bn > 128) continue;
+      if (bn > 64 && N <= 64) continue;
+      if (g_force[1] > 0 && bn != g_force[1]) continue;
+      for (int si = 0; si < 8; ++si) {
+        const int sp = kSplits[si];
+        if (g_force[2] > 0 && sp != (g_force[2] > nk ? nk : g_force[2])) continue;
+        if (sp > 1 && (!split_ok || sp > max_planes || sp * ctas > MAX_CLUSTER || nk / sp < 3)) continue;
+        const float us = predict_us(M, N, nk, ctas, bn, sp);
+        if (us < best) best = us, c.ctas = ctas, c.bn = bn, c.splits = sp;
+      }
     }
-    if (g_force[2] > 0) c.splits = g_force[2] > nk ? nk : g_force[2];
-    if (c.splits > max_planes) c.splits = max_planes;
+  }
+  if (best > 1e29f) {   // a forced configuration that is not available: fall back to the nearest valid one
+    c.ctas = (g_force[0] == 1) ? 1 : 2;
+    c.bn = (g_force[1] == 64 || g_force[1] == 128 || (c.ctas == 2 && (g_force[1] == 160 || g_force[1] == 256))) ? g_force[1] : 128;
+    c.splits = 1;
   }
   return c;
 }
@@ -943,12 +1031,16 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, GemmParams p, int batch, 
   static PerDeviceOnce attr;
   if (attr.need()) {
     O2345_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CTAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (MODE == 3)   // split-K clusters of up to 16 CTAs
+      O2345_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CTAS, MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   p.bn = BN, p.ctas = CTAS, p.mode = MODE;
   p.diag = diag_buffer(st);
   const int mblocks = CTAS == 2 ? 2 * cdiv(p.M, 2 * BM) : cdiv(p.M, BM);
-  dim3 grid(mblocks, cdiv(p.N, BN), batch > 0 ? batch : (p.splits > 1 ? p.splits : 1));
-  O2345_CUDA(launch_pdl_cluster(gemm_tc_kernel<BN, STAGES, CTAS, MODE>, grid, dim3(GEMM_THREADS), (size_t)SMEM, st, CTAS, a, b, p));
+  const int splits = (MODE == 3 && batch == 0 && p.splits > 1) ? p.splits : 1;
+  p.splits = splits;
+  dim3 grid(mblocks, cdiv(p.N, BN), batch > 0 ? batch : splits);
+  O2345_CUDA(launch_pdl_cluster(gemm_tc_kernel<BN, STAGES, CTAS, MODE>, grid, dim3(GEMM_THREADS), (size_t)SMEM, st, CTAS, splits, a, b, p));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
@@ -966,6 +1058,10 @@ int launch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const Gemm
 }
 
 int dispatch(const Config& c, int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
+  if (p.colstats && mode == 3 && c.splits <= 1) {
+    set_error("o2345_gemm_f16: column statistics need the staged fp16 epilogue (16-byte aligned C / residual) or split-K");
+    return O2345_EUNSUPPORTED;
+  }
   if (c.ctas == 2) {
     if (c.bn == 64) return launch_mode<64, 5, 2>(mode, a, b, p, batch, st);
     if (c.bn == 128) return launch_mode<128, 4, 2>(mode, a, b, p, batch, st);
@@ -990,15 +1086,17 @@ int fill_epilogue(GemmParams& p, const o2345_epilogue* ep, int M, int N, int64_t
   p.bias = ep->bias, p.rowbias = reinterpret_cast<const __half*>(ep->rowbias), p.rowbias_ld = ep->rowbias_ld;
   p.rows_per_group = ep->rowbias ? ep->rows_per_group : 1;
   p.residual = reinterpret_cast<const __half*>(ep->residual), p.out_f32 = ep->out_f32, p.act = ep->act, p.alpha = ep->alpha;
-  (void)M;
+  if (ep->colstats) {
+    O2345_CHECK_ARG(ep->act == 0 && !ep->out_f32 && (N % 8) == 0 && (ldc % 8) == 0,
+                    "column statistics: fp16 output without activation, N and ldc multiples of 8");
+    O2345_CHECK_ARG(ep->stats_rows_per_group > 0 && ((ep->stats_rows_per_group % 128) == 0 || ep->stats_rows_per_group == 64),
+                    "column statistics: rows per group must be 64 or a multiple of 128");
+    p.colstats = ep->colstats, p.stats_rpg = ep->stats_rows_per_group, p.stats_groups = cdiv(M, ep->stats_rows_per_group);
+  }
   return O2345_OK;
 }
 
-void set_workspace(GemmParams& p, float* ws, int64_t ws_floats) {
-  p.ws = ws;
-  p.tickets = (ws && ws_floats > TICKET_INTS) ? reinterpret_cast<int*>(ws + (ws_floats - TICKET_INTS)) : nullptr;
-  if (!p.tickets) p.ws = nullptr;
-}
+void set_workspace(GemmParams& p, float* ws, int64_t ws_floats) { p.ws = ws_floats > 0 ? ws : nullptr; }
 
 }  // namespace
 }  // namespace o2345
@@ -1009,6 +1107,10 @@ extern "C" void o2345_debug_gemm_trace(long long* device_buf16) { g_trace = devi
 
 extern "C" void o2345_debug_gemm_force(int ctas, int bn, int splits) {
   g_force[0] = ctas, g_force[1] = bn, g_force[2] = splits;
+}
+
+extern "C" void o2345_debug_gemm_model(const float* seven) {
+  for (int i = 0; i < 7; ++i) g_model[i] = seven[i];
 }
 
 extern "C" int o2345_last_trap(char* buf, size_t n) {

@@ -32,7 +32,7 @@ class Views(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("bias", c_fp), ("residual", c_fp), ("rowbias", c_fp), ("rowbias_ld", c_i64), ("rows_per_group", C.c_int),
-                ("act", C.c_int), ("alpha", C.c_float), ("out_f32", C.c_int)]
+                ("act", C.c_int), ("alpha", C.c_float), ("out_f32", C.c_int), ("colstats", c_fp), ("stats_rows_per_group", C.c_int)]
 
 
 PTS_EXPLICIT, PTS_LATTICE, PTS_RAYS = 0, 1, 2
@@ -83,6 +83,7 @@ _SIGS = {
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
     "o2345_debug_gemm_trace": (None, [c_fp]),
     "o2345_debug_gemm_force": (None, [C.c_int, C.c_int, C.c_int]),
+    "o2345_debug_gemm_model": (None, [C.POINTER(C.c_float)]),
     "o2345_last_trap": (C.c_int, [C.c_char_p, C.c_size_t]),
     "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64,
                                     C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
@@ -91,6 +92,8 @@ _SIGS = {
                                         c_fp]),
     "o2345_norm_act_im2col": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp,
                                         C.c_int, c_fp, c_fp]),
+    "o2345_norm_act_im2col_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,
+                                              c_fp, C.c_int, C.c_float, c_fp, c_fp, C.c_int, c_fp, c_fp]),
     "o2345_layernorm_rows": (C.c_int, [c_fp, c_i64, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp]),
     "o2345_softmax_rows": (C.c_int, [c_fp, c_i64, C.c_int, c_fp, c_fp]),
     "o2345_attention_f16": (C.c_int, [c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,

@@ -20,20 +20,11 @@ import struct
 import numpy as np
 
 
-def merge_vertices(vertices, triangles, colors=None, digits=8, lattice_positions=None):
-    """lattice_positions (optional): the same vertices in marching-cubes INDEX units.  Marching cubes emits one vertex per
-    sign-changing lattice edge, so two of its vertices can only coincide at a lattice point both of their edges touch: when
-    fewer than two vertices lie within 1e-5 voxels of a lattice point nothing can merge and the (sort-based, ~0.2 s for
-    2 M vertices) general path is skipped -- the usual case."""
+def merge_vertices(vertices, triangles, colors=None, digits=8):
     v = np.asarray(vertices, np.float64)
     f = np.asarray(triangles, np.int64).reshape(-1, 3)
     if len(v) == 0 or len(f) == 0:
         return v, f, colors
-    if lattice_positions is not None:
-        li = np.asarray(lattice_positions)
-        near = (np.abs(li - np.rint(li)).max(axis=1) < 1e-5)
-        if int(near.sum()) < 2:
-            return v, f, colors
     key = np.round(v * 10.0 ** digits).astype(np.int64)
     _, first, inverse = np.unique(key, axis=0, return_index=True, return_inverse=True)
     inverse = np.asarray(inverse).reshape(-1)

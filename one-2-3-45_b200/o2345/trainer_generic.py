@@ -119,7 +119,6 @@ class GenericTrainer(nn.Module):
             density_or_sdf_network, bmin, bmax, resolution=resolution, threshold=threshold,
             device=conditional_volume.device, conditional_volume=conditional_volume, lod=lod,
             occupancy_mask=occupancy_mask)
-        vertices_unit = vertices
         vt = torch.tensor(vertices).to(conditional_volume)
         rgb, _ = self.sdf_renderer_lod0.blend_points(vt, density_or_sdf_network, rendering_network, conditional_volume,
                                                      conditional_valid_mask_volume, feature_maps, color_maps, w2cs,
@@ -132,11 +131,11 @@ class GenericTrainer(nn.Module):
             vh = np.concatenate([vertices, np.ones_like(vertices[:, :1])], axis=1)
             vertices = (vh @ tm.T)[:, :3]
         colors = (rgb.cpu() * 255).numpy().astype(np.uint8)
-        # trimesh.Trimesh(vertices, triangles, vertex_colors=...) with its default process=True merges coincident
-        # vertices before the export (reference :1374-1380)
-        lo, hi = np.asarray(bound_min, np.float64), np.asarray(bound_max, np.float64)
-        lattice = (vertices_unit - lo[None]) / (hi - lo)[None] * (resolution - 1.0)
-        vertices, triangles, colors = merge_vertices(vertices, triangles, colors, lattice_positions=lattice)
+        # trimesh.Trimesh(vertices, triangles, vertex_colors=...) with its default process=True merges coincident vertices
+        # before the export (reference :1374-1380).  Marching-cubes vertices can only coincide on lattice points; the
+        # renderer counted how many sit on one (on the device): fewer than two -> nothing to merge, arrays untouched.
+        if getattr(self.sdf_renderer_lod0, "mc_vertices_on_lattice", 2) >= 2:
+            vertices, triangles, colors = merge_vertices(vertices, triangles, colors)
         if self.base_exp_dir is not None:
             os.makedirs(self.base_exp_dir, exist_ok=True)
             write_ply(os.path.join(self.base_exp_dir, 'mesh.ply'), vertices, triangles, colors)

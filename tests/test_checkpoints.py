@@ -178,10 +178,6 @@ def test_mesh_tail_merge_and_formats(tmp_path):
     assert len(v2) == 4 and f2.max() == 3
     assert np.array_equal(v2[f2], v[f])                                   # same triangles in space
     assert np.array_equal(c2[1], c[1])                                    # the first occurrence keeps its colour
-    # marching-cubes fast path: no vertex on a lattice point -> nothing can coincide, arrays returned untouched
-    lat = np.array([[0.5, 0, 0], [1.5, 0, 0], [0, 0.5, 0], [1, 0.25, 0], [1, 1, 0.5], [3, 3, 3.5]])
-    v3, f3, _ = merge_vertices(v, f, c, lattice_positions=lat)
-    assert v3 is not None and len(v3) == 6
     write_ply(str(tmp_path / "mesh.ply"), v2, f2, c2)
     rv, rf, rc = read_ply(str(tmp_path / "mesh.ply"))
     assert np.allclose(rv, v2) and np.array_equal(rf, f2) and np.array_equal(rc[:, :3], c2)

@@ -2,7 +2,7 @@
 oracle/pin_clip_against_hf.py froze (Hugging Face transformers' implementation, fp32, same seeded weights).
 
 Tolerance: 24 pre-LN transformer layers with fp16 activations (the reference runs the tower in fp16 under
---half_precision as well); the embedding has std 0.68 and |max| 2.5, the bar is max |err| < 0.05, mean < 0.01."""
+--half_precision as well); the embedding has std 0.68 and |max| 2.5, the bar is 3x the measured deviation: max |err| < 1.2e-2, mean < 2.1e-3."""
 import os
 
 import numpy as np
@@ -48,7 +48,7 @@ def test_embedding_matches_golden(clip_net, gold):
     assert e.shape == (1, 768) and e.dtype == torch.float32
     err = (e.cpu() - torch.from_numpy(gold["embed"])).abs()
     print("clip: max err", float(err.max()), "mean err", float(err.mean()))
-    assert float(err.max()) < 0.05 and float(err.mean()) < 0.01
+    assert float(err.max()) < 1.2e-2 and float(err.mean()) < 2.1e-3     # 3x the measured 3.7e-3 / 7e-4
     c = clip_net.encode(torch.cat([x, -x]))                  # batch of two, encode() adds the token axis
-    assert c.shape == (2, 1, 768) and float((c[0, 0].cpu() - torch.from_numpy(gold["embed"][0])).abs().max()) < 0.05
+    assert c.shape == (2, 1, 768) and float((c[0, 0].cpu() - torch.from_numpy(gold["embed"][0])).abs().max()) < 1.2e-2
     assert clip_net([""]).shape == (1, 768) and float(clip_net([""]).abs().max()) == 0.0

@@ -1,0 +1,249 @@
+"""GPU parity at the BASELINE.json configurations (the mini-configuration tests live in test_gpu_parity.py).
+
+configs[0]: 8 pre-rendered 256x256 views -> 64^3 SDF grid, 1024 rays x 64 samples (the reference's CPU-runnable case):
+            CUDA path against the CPU oracle on the same seeded inputs.
+configs[1]: 32 views of 256x256 -> 96^3 volume (the bench configuration): frustum mask and occupancy BIT-EXACT against the
+            oracle, the whole conditional volume, 4 096 SDF points + gradients, 256 rays x (64+64) samples, 512 vertex
+            colours; a 5-iteration DDIM trajectory of the REAL 859.5 M-parameter UNet against the fp32 oracle with injected
+            noise; two different scenes rendered by one renderer object in one process (stale-cache hazard).
+configs[3]: 32 views, 192^3 grid, 4096 rays x 128 samples: size-independent properties only (the oracle would take
+            minutes): occupancy ratio, sortedness, finite colours, lattice == explicit points.
+Tolerances are stated at each assertion (fp32 path B: integer outputs bit-exact, floats a few 1e-4; fp16 path A: <= 3x the
+measured deviation from the fp32 oracle).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import states_torch, t
+from o2345 import synthetic as S
+from oracle import recon_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def scene(n_views, hw, seed):
+    meta = S.pose_json(60.0)
+    k = np.array(meta["intrinsics"])
+    k[:2] *= hw / 256.0
+    meta["intrinsics"] = k.tolist()
+    cams = S.scene_cameras(meta, n_src=n_views, img_wh=(hw, hw))
+    imgs = S.images(n_views + 1, hw, hw, seed=seed)
+    return cams, imgs
+
+
+def test_config0_against_oracle():
+    from o2345.pipeline import build_networks
+    dev = torch.device("cuda:0")
+    D, V, HW, R, NS = 64, 8, 256, 1024, 32
+    st = states_torch(0)
+    cams, imgs = scene(V, HW, 11)
+    src = t(imgs[1:])
+    fm_ref = O.pyramid_feature_maps(src, st["pyramid_feature_network"])
+    cv = O.conditional_volume(fm_ref, t(cams["partial_vol_origin"]), t(cams["affine_mats"]), st["sdf_network_lod0"], D,
+                              2.0 / (D - 1), HW, HW)
+    tr = build_networks(dev, vol_dim=D, states=S.all_states(0), n_samples=NS, n_importance=NS, perturb=0.0)
+    fm = tr.obtain_pyramid_feature_maps(src.to(dev))
+    cond = tr.sdf_network_lod0.get_conditional_volume(fm[None], t(cams["partial_vol_origin"]).to(dev)[None],
+                                                      t(cams["affine_mats"]).to(dev)[None], sizeH=HW, sizeW=HW)
+    assert torch.equal(cond["valid_mask_volume_scale0"].cpu() > 0, cv["occ"] > 0)              # occupancy: bit-exact
+    assert float((cond["dense_volume_scale0"].cpu() - cv["dense"]).abs().max()) < 1e-3
+    ro, rv = S.query_rays(cams["query_intrinsic"], cams["query_c2w"], HW, HW)
+    sel = np.linspace(0, HW * HW - 1, R).astype(np.int64)
+    near, far = t(cams["query_near_far"][:1]), t(cams["query_near_far"][1:])
+    res = tr.sdf_renderer_lod0.render(t(ro[sel]).to(dev), t(rv[sel]).to(dev), near.to(dev), far.to(dev), tr.sdf_network_lod0,
+                                      tr.rendering_network_lod0, perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0,
+                                      lod=0, conditional_volume=cond["dense_volume_scale0"],
+                                      conditional_valid_mask_volume=cond["valid_mask_volume_scale0"], feature_maps=fm,
+                                      color_maps=src.to(dev), w2cs=t(cams["w2cs"]).to(dev), intrinsics=t(cams["intrinsics"]).to(dev),
+                                      img_wh=[HW, HW], query_c2w=t(cams["query_c2w"])[None].to(dev))
+    ref = O.render_rays(t(ro[sel]), t(rv[sel]), near, far, cond["dense_volume_scale0"].cpu(), cond["valid_mask_volume_scale0"].cpu(),
+                        fm.cpu(), src, t(cams["w2cs"]), t(cams["intrinsics"]), t(cams["query_c2w"])[None], st["sdf_network_lod0"],
+                        st["rendering_network_lod0"], st["variance_network_lod0"]["variance"], W=HW, H=HW, n_samples=NS,
+                        n_importance=NS)
+    dz = (res["z_vals"].cpu() - ref["z"]).abs().max(dim=1)[0]
+    same = dz < 1e-5
+    print("config0: rays with identical depth draws", int(same.sum()), "of", R)
+    assert float(same.float().mean()) > 0.5
+    assert float((res["color_fine"].cpu()[same] - ref["color"][same]).abs().max()) < 5e-4
+    assert float((res["depth"].cpu()[same] - ref["depth"][same]).abs().max()) < 5e-4
+    assert float((res["color_fine"].cpu() - ref["color"]).abs().max()) < 1e-2
+
+
+def test_config3_properties():
+    from o2345.pipeline import build_networks, synthetic_sample
+    dev = torch.device("cuda:0")
+    D = 192
+    tr = build_networks(dev, vol_dim=D, states=S.all_states(0), perturb=0.0)
+    sample = synthetic_sample(dev, n_views=32, H=256, W=256)
+    imgs, fmaps, cond, sizeW, sizeH = tr._conditional_features(sample)
+    occ = cond["valid_mask_volume_scale0"]
+    frac = float((occ > 0).float().mean())
+    print("config3: occupied fraction of the 192^3 lattice", frac)
+    assert 0.5 < frac < 1.0
+    ro = sample["rays"]["rays_o"][0][::16][:4096].contiguous()
+    rd = sample["rays"]["rays_v"][0][::16][:4096].contiguous()
+    near, far = sample["query_near_far"][0, :1], sample["query_near_far"][0, 1:]
+    out = tr.sdf_renderer_lod0.render(ro, rd, near, far, tr.sdf_network_lod0, tr.rendering_network_lod0, perturb_overwrite=0,
+                                      background_rgb=1.0, alpha_inter_ratio=1.0, lod=0,
+                                      conditional_volume=cond["dense_volume_scale0"], conditional_valid_mask_volume=occ,
+                                      feature_maps=fmaps, color_maps=imgs, w2cs=sample["w2cs"][0],
+                                      intrinsics=sample["intrinsics"][0], img_wh=[256, 256], query_c2w=sample["query_c2w"])
+    z, c = out["z_vals"], out["color_fine"]
+    assert z.shape == (4096, 128) and torch.all(z[:, 1:] >= z[:, :-1])
+    assert torch.isfinite(c).all() and float(c.min()) >= -1e-4 and float(c.max()) <= 1 + 1e-4
+    u = tr.sdf_renderer_lod0.extract_fields([-1] * 3, [1] * 3, 96, None, dev, conditional_volume=cond["dense_volume_scale0"], lod=0)
+    lin = torch.linspace(-1, 1, 96, device=dev)
+    idx = torch.randint(0, 96, (2048, 3), device=dev)
+    pts = torch.stack([lin[idx[:, 0]], lin[idx[:, 1]], lin[idx[:, 2]]], -1)
+    s = tr.sdf_network_lod0.sdf(pts, cond["dense_volume_scale0"], 0)["sdf_pts_scale0"][:, 0]
+    assert float((-u[idx[:, 0], idx[:, 1], idx[:, 2]] - s).abs().max()) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------ configs[1]: 96^3 / 32 views
+@pytest.fixture(scope="module")
+def c1():
+    """Oracle and CUDA path side by side at the bench configuration (oracle: ~20 s of host time)."""
+    from o2345.pipeline import build_networks
+    dev = torch.device("cuda:0")
+    D, V, HW = 96, 32, 256
+    st = states_torch(0)
+    cams, imgs = scene(V, HW, 1234)
+    src = t(imgs[1:])
+    origin, proj = t(cams["partial_vol_origin"]), t(cams["affine_mats"])
+    fm_ref = O.pyramid_feature_maps(src, st["pyramid_feature_network"])
+    cv = O.conditional_volume(fm_ref, origin, proj, st["sdf_network_lod0"], D, 2.0 / (D - 1), HW, HW)
+    tr = build_networks(dev, vol_dim=D, states=S.all_states(0), perturb=0.0)
+    fm = tr.obtain_pyramid_feature_maps(src.to(dev))
+    cond = tr.sdf_network_lod0.get_conditional_volume(fm[None], origin.to(dev)[None], proj.to(dev)[None], sizeH=HW, sizeW=HW)
+    torch.cuda.synchronize()
+    return dict(dev=dev, D=D, V=V, HW=HW, st=st, cams=cams, src=src, fm_ref=fm_ref, cv=cv, tr=tr, fm=fm, cond=cond,
+                origin=origin, proj=proj)
+
+
+def test_config1_frustum_mask_and_occupancy_bit_exact(c1):
+    D, HW = c1["D"], c1["HW"]
+    occ_gpu = c1["cond"]["valid_mask_volume_scale0"].cpu() > 0
+    assert torch.equal(occ_gpu, c1["cv"]["occ"] > 0)                       # 884 736 voxels, every one
+    last = c1["tr"].sdf_network_lod0._last
+    n = int(last["count"].item())
+    rows = last["rows"][:n].cpu().long()
+    assert n == int((c1["cv"]["occ"] > 0).sum())                           # the same voxels survive the >= 2-view rule
+    assert bool((rows[1:] > rows[:-1]).all())                              # ascending x*D^2 + y*D + z, the reference's row order
+    assert torch.equal(rows, torch.nonzero((c1["cv"]["occ"] > 0).reshape(-1))[:, 0])
+    # per-(voxel, view) frustum bits against the oracle's projection, all 884 736 x 32 of them
+    mask_ref = O.project_voxels(O.lattice_coords(D), c1["origin"], 2.0 / (D - 1), c1["proj"], HW, HW)[3]     # [N, V] int32
+    bits = last["mask_bits"].cpu()
+    got = torch.stack([(bits >> v) & 1 for v in range(c1["V"])], 1)       # bit v of a voxel's word = view v sees it
+    assert torch.equal(got.bool(), mask_ref.bool())
+
+
+def test_config1_feature_maps_and_conditional_volume(c1):
+    assert float((c1["fm"].cpu() - c1["fm_ref"]).abs().max()) < 1e-4       # FeatureNet pyramid, [32, 56, 256, 256]
+    err = (c1["cond"]["dense_volume_scale0"].cpu() - c1["cv"]["dense"]).abs()
+    print("config1: conditional volume max err", float(err.max()), "mean", float(err.mean()))
+    assert float(err.max()) < 1e-3 and float(err.mean()) < 2e-5            # variance = E[f^2] - E[f]^2 cancellation + 10 sparse convs
+
+
+def test_config1_sdf_points_rays_and_vertices(c1):
+    dev, tr, cams, st, HW = c1["dev"], c1["tr"], c1["cams"], c1["st"], c1["HW"]
+    vol, occ = c1["cond"]["dense_volume_scale0"], c1["cond"]["valid_mask_volume_scale0"]
+    g = np.random.default_rng(3)
+    pts = t(g.uniform(-1.02, 1.02, size=(4096, 3)).astype(np.float32))
+    out = tr.sdf_network_lod0.sdf(pts.to(dev), vol, 0)
+    grad = tr.sdf_network_lod0.gradient(pts.to(dev), vol, 0)
+    s_ref, f_ref, _ = O.sdf_query(pts, vol.cpu(), st["sdf_network_lod0"])
+    g_ref = O.sdf_gradient(pts, vol.cpu(), st["sdf_network_lod0"])
+    assert float((out["sdf_pts_scale0"].cpu() - s_ref).abs().max()) < 5e-5
+    assert float((out["sdf_features_pts_scale0"].cpu() - f_ref).abs().max()) < 1e-4
+    assert float((grad.cpu()[:, 0] - g_ref).abs().max()) < 5e-4
+    # 256 rays x (64 + 64) samples x 32 views
+    ro, rv = S.query_rays(cams["query_intrinsic"], cams["query_c2w"], HW, HW)
+    sel = np.linspace(0, HW * HW - 1, 256).astype(np.int64)
+    near, far = t(cams["query_near_far"][:1]), t(cams["query_near_far"][1:])
+    kw = dict(perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0, lod=0, conditional_volume=vol,
+              conditional_valid_mask_volume=occ, feature_maps=c1["fm"], color_maps=c1["src"].to(dev), w2cs=t(cams["w2cs"]).to(dev),
+              intrinsics=t(cams["intrinsics"]).to(dev), img_wh=[HW, HW], query_c2w=t(cams["query_c2w"])[None].to(dev))
+    res = tr.sdf_renderer_lod0.render(t(ro[sel]).to(dev), t(rv[sel]).to(dev), near.to(dev), far.to(dev), tr.sdf_network_lod0,
+                                      tr.rendering_network_lod0, **kw)
+    ref = O.render_rays(t(ro[sel]), t(rv[sel]), near, far, vol.cpu(), occ.cpu(), c1["fm"].cpu(), c1["src"], t(cams["w2cs"]),
+                        t(cams["intrinsics"]), t(cams["query_c2w"])[None], st["sdf_network_lod0"], st["rendering_network_lod0"],
+                        st["variance_network_lod0"]["variance"], W=HW, H=HW)
+    same = (res["z_vals"].cpu() - ref["z"]).abs().max(dim=1)[0] < 1e-5     # rays whose 4 importance rounds drew identical depths
+    print("config1: rays with identical depth draws", int(same.sum()), "of 256")
+    assert float(same.float().mean()) > 0.5
+    assert float((res["color_fine"].cpu()[same] - ref["color"][same]).abs().max()) < 1e-3   # default blend kernel: fp16 tensor-core operands
+    assert float((res["depth"].cpu()[same] - ref["depth"][same]).abs().max()) < 5e-4
+    assert float((res["color_fine"].cpu() - ref["color"]).abs().max()) < 2e-2
+    # 512 mesh-vertex colours (Projector.compute_view_independent + blending network)
+    verts = t(g.uniform(-0.7, 0.7, size=(512, 3)).astype(np.float32))
+    rgb, nrm = tr.sdf_renderer_lod0.blend_points(verts.to(dev), tr.sdf_network_lod0, tr.rendering_network_lod0, vol, occ, c1["fm"],
+                                                 c1["src"].to(dev), t(cams["w2cs"]).to(dev), t(cams["intrinsics"]).to(dev), [HW, HW])
+    rgb_ref, nrm_ref = O.vertex_colors(verts, vol.cpu(), occ.cpu(), c1["fm"].cpu(), c1["src"], t(cams["w2cs"]), t(cams["intrinsics"]),
+                                       st["sdf_network_lod0"], st["rendering_network_lod0"], W=HW, H=HW)
+    assert float((rgb.cpu() - rgb_ref).abs().max()) < 2e-3 and float((nrm.cpu() - nrm_ref).abs().max()) < 1e-3
+
+
+def test_two_scenes_through_one_renderer(c1):
+    """The renderer caches channel-last source maps: a second scene in the same process (fresh tensors, possibly at recycled
+    addresses) must not be rendered with the first scene's maps."""
+    from o2345.pipeline import build_networks
+    dev, tr, HW = c1["dev"], c1["tr"], c1["HW"]
+
+    def render(trainer, seed):
+        cams, imgs = scene(32, HW, seed)
+        src = t(imgs[1:]).to(dev)
+        fm = trainer.obtain_pyramid_feature_maps(src)
+        cond = trainer.sdf_network_lod0.get_conditional_volume(fm[None], t(cams["partial_vol_origin"]).to(dev)[None],
+                                                               t(cams["affine_mats"]).to(dev)[None], sizeH=HW, sizeW=HW)
+        ro, rv = S.query_rays(cams["query_intrinsic"], cams["query_c2w"], HW, HW)
+        sel = np.linspace(0, HW * HW - 1, 128).astype(np.int64)
+        out = trainer.sdf_renderer_lod0.render(
+            t(ro[sel]).to(dev), t(rv[sel]).to(dev), t(cams["query_near_far"][:1]).to(dev), t(cams["query_near_far"][1:]).to(dev),
+            trainer.sdf_network_lod0, trainer.rendering_network_lod0, perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio=1.0,
+            lod=0, conditional_volume=cond["dense_volume_scale0"], conditional_valid_mask_volume=cond["valid_mask_volume_scale0"],
+            feature_maps=fm, color_maps=src, w2cs=t(cams["w2cs"]).to(dev), intrinsics=t(cams["intrinsics"]).to(dev),
+            img_wh=[HW, HW], query_c2w=t(cams["query_c2w"])[None].to(dev))
+        return out["color_fine"].clone()
+    first = render(tr, 77)
+    del first
+    torch.cuda.empty_cache()
+    second = render(tr, 78)                                  # same renderer object, different images
+    fresh = render(build_networks(dev, vol_dim=96, states=S.all_states(0), perturb=0.0), 78)
+    assert float((second - fresh).abs().max()) < 1e-6
+
+
+def test_real_unet_ddim_trajectory_against_oracle():
+    """Five DDIM iterations (S = 5, eta = 1, CFG 3) of the real UNet on the tcgen05 path against ldm_oracle.ddim_sample
+    running the fp32 oracle UNet on the host, same weights, same injected noise.  fp16 rounding of ~60 layers re-enters the
+    loop four times: measured max |x - x_oracle| 6e-3 on latents of std ~1 (bar: 2e-2 max, 3e-3 mean)."""
+    from o2345.ddim import DDIMSampler
+    from o2345.zero123 import build_zero123
+    from oracle import ldm_oracle as LO
+    dev = torch.device("cuda:0")
+    model = build_zero123(dev, seed=0)                         # fp32 schedule buffers (no .half()): the oracle uses the fp32 table
+    sd = {k: torch.from_numpy(v) for k, v in S.unet_state(0).items()}
+    B = 1
+    g = torch.Generator().manual_seed(5)
+    cond = {"c_crossattn": [torch.randn(B, 1, 768, generator=g)], "c_concat": [torch.randn(B, 4, 32, 32, generator=g)]}
+    uc = {"c_crossattn": [torch.zeros(B, 1, 768)], "c_concat": [torch.zeros(B, 4, 32, 32)]}
+    x_T = torch.randn(B, 4, 32, 32, generator=g)
+    n_it = len(LO.ddim_schedule(LO.linear_beta_alphas_cumprod(), 5, 1.0)[0]) - 1
+    noises = [torch.randn(B, 4, 32, 32, generator=g) for _ in range(n_it)]
+
+    def apply_cpu(x, tt, c):
+        return LO.unet_forward(sd, torch.cat([x, c["c_concat"][0]], 1), tt, c["c_crossattn"][0])
+    with torch.no_grad():
+        want = LO.ddim_sample(apply_cpu, x_T, cond, uc, 3.0, LO.linear_beta_alphas_cumprod(), 5, 1.0, noises)
+    to = lambda d: {k: [v[0].to(dev)] for k, v in d.items()}
+    it = iter(noises)
+    real = torch.randn
+    torch.randn = lambda *a, **k: next(it).to(dev)
+    try:
+        got, _ = DDIMSampler(model).sample(S=5, batch_size=B, shape=[4, 32, 32], conditioning=to(cond), verbose=False, eta=1.0,
+                                           x_T=x_T.to(dev), unconditional_guidance_scale=3.0, unconditional_conditioning=to(uc))
+    finally:
+        torch.randn = real
+    err = (got.cpu() - want).abs()
+    print("real-UNet DDIM trajectory: max", float(err.max()), "mean", float(err.mean()), "std of x", float(want.std()))
+    assert float(err.max()) < 2e-2 and float(err.mean()) < 3e-3

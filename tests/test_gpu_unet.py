@@ -2,7 +2,8 @@
 
 Tolerance: the reference itself runs this model in fp16 under autocast (fp32 GroupNorm / LayerNorm / softmax); the
 golden vector is the reference's fp32 CPU output.  fp16 storage of ~60 layers gives ~1e-2 relative deviations, so
-the bar is max |err| < 0.02 and mean |err| < 0.004 on an output of std 0.38 (measured: 0.002 / 0.0004; a wrong layer gives O(1))."""
+the bar is 3x the measured deviation: max |err| < 6.5e-3 and mean |err| < 1.2e-3 on an output of std 0.38 (measured: 2.1e-3 / 3.9e-4;
+a missing bias in one layer moves the output by > 1e-2, a wrong layer by O(1))."""
 import os
 
 import numpy as np
@@ -35,7 +36,7 @@ def test_unet_matches_reference_golden(unet, gold):
     assert e.shape == (2, 4, 32, 32) and e.dtype == torch.float32
     err = (e.cpu() - torch.from_numpy(gold["unet_eps"])).abs()
     print("unet: max err", float(err.max()), "mean err", float(err.mean()))
-    assert float(err.max()) < 0.02 and float(err.mean()) < 0.004
+    assert float(err.max()) < 6.5e-3 and float(err.mean()) < 1.2e-3     # 3x the measured 2.1e-3 / 3.9e-4
 
 
 def test_unet_batch8_is_consistent_with_batch2(unet):

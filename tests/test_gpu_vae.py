@@ -26,13 +26,13 @@ def test_decode_and_encode_match_reference(vae):
     assert img.shape == (1, 3, 256, 256)
     err = (img.cpu()[:, :, ::4, ::4] - torch.from_numpy(gold["dec"])).abs()
     print("decode: max", float(err.max()), "mean", float(err.mean()))
-    assert float(err.max()) < 0.05 and float(err.mean()) < 0.01
+    assert float(err.max()) < 1.8e-2 and float(err.mean()) < 3e-3       # 3x the measured 5.8e-3 max (images in [-1, 1])
     post = vae.encode(torch.from_numpy(x).cuda())
     m = torch.cat([post.mean, post.logvar], 1)
     err = (m.cpu() - torch.from_numpy(gold["moments"])).abs()
     print("encode: max", float(err.max()), "mean", float(err.mean()))
     assert post.mode().shape == (1, 4, 32, 32)
-    assert float(err.max()) < 0.05 and float(err.mean()) < 0.01
+    assert float(err.max()) < 1.8e-2 and float(err.mean()) < 3e-3
 
 
 def test_vae_oracle_agrees_on_another_input(vae):

@@ -107,7 +107,7 @@ for k, calls in groups.items():
                     continue
                 mblocks = (M + 127) // 128 if ctas == 1 else 2 * ((M + 255) // 256)
                 tiles = mblocks * ((N + bn - 1) // bn)
-                if sp > 1 and tiles * sp > 700:
+                if sp > 1 and (tiles * sp > 700 or sp * ctas > 16):
                     continue
                 if QUICK and sp not in (1, 2, 4, 8):
                     continue
