@@ -210,7 +210,9 @@ def test_two_scenes_through_one_renderer(c1):
     torch.cuda.empty_cache()
     second = render(tr, 78)                                  # same renderer object, different images
     fresh = render(build_networks(dev, vol_dim=96, states=S.all_states(0), perturb=0.0), 78)
-    assert float((second - fresh).abs().max()) < 1e-6
+    # stale maps would give O(0.1-1) colour differences; two correct runs differ only by the summation order of the
+    # BatchNorm / cost-volume atomics (measured 2.5e-5)
+    assert float((second - fresh).abs().max()) < 1e-3
 
 
 def test_real_unet_ddim_trajectory_against_oracle():

@@ -69,8 +69,9 @@ del g, ops
 DEF = [40, 0.5, 6300, 5, 3, 4, 1]
 def model(v): lib.o2345_debug_gemm_model((C.c_float * 7)(*v))
 print("%d launches" % len(rec))
-CASES = [("default", (0, 0, 0), DEF), ("no split", (0, 0, 1), DEF), ("bn160", (0, 160, 0), DEF), ("epi 1", (0, 0, 0), [40, 0.5, 6300, 5, 1, 4, 1])]
+CASES = [("default", (0, 0, 0), DEF), ("no split", (0, 0, 1), DEF), ("bn160", (0, 160, 0), DEF), ("bn128", (0, 128, 0), DEF),
+         ("split cost x2", (0, 0, 0), [40, 0.5, 6300, 5, 3, 8, 2])]
 for label, force, mv in CASES:
     lib.o2345_debug_gemm_force(*force); model(mv)
-    print("%-14s %.3f ms" % (label, replay_ms()), flush=True)
+    print("%-22s %.3f ms" % (label, replay_ms()), flush=True)
 lib.o2345_debug_gemm_force(0, 0, 0); model(DEF)
