@@ -37,7 +37,7 @@ H = W = 256
 N_VIEWS = 32
 VOL = 96
 N_RAYS = H * W
-CHUNK = 8192
+CHUNK = 65536   # rays marched per launch group (the reference uses 512; results are per-ray, the chunk only sets the launch count)
 MESH_RES = 256
 UNET_ITERS = 2 * 76 + 8 * 49
 CONFIG = {"workload": "configs[1]: single 256x256 image -> mesh: Zero123 75/50-step DDIM fp16 (544 UNet iterations at batch 8) "
@@ -301,6 +301,24 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
     n_gemm = len(rec)
     del graph
     beat("stage breakdown: %d GEMM launches of one UNet iteration replay in %.3f ms" % (n_gemm, ms_gemm))
+    # informational (SURVEY.md 2a "beats PyTorch / cuDNN on the same box"): the plain-PyTorch restatement of the same UNet
+    # (oracle/ldm_oracle.py: F.conv2d / F.linear / einsum attention -> cuDNN + cuBLAS) under fp16 autocast on this GPU, eager,
+    # outside every timed region.  It is the reference's execution model, not the product path.
+    ms_torch = None
+    if int(os.environ.get("RANK", 0)) == 0:
+        try:
+            from o2345 import synthetic as S
+            from oracle import ldm_oracle as LO
+            sd_t = {k: torch.from_numpy(v).to(dev) for k, v in S.unet_state(0).items()}
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                for _ in range(2):
+                    LO.unet_forward(sd_t, x, t, ctx)
+                ms_torch = float(np.median([ev_time(lambda: LO.unet_forward(sd_t, x, t, ctx))[0] for _ in range(5)]))
+            del sd_t
+            torch.cuda.empty_cache()
+            beat("stage breakdown: plain PyTorch (cuDNN / cuBLAS, fp16 autocast, eager) UNet iteration %.2f ms" % ms_torch)
+        except Exception as e:
+            beat("stage breakdown: plain-PyTorch UNet timing skipped: %r" % (e,))
     z = torch.randn(4, 4, 32, 32, device=dev)
     vae.decode(z)
     ms_dec = float(np.mean([ev_time(lambda: vae.decode(z))[0] for _ in range(3)]))
@@ -326,7 +344,7 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
     torch.cuda.synchronize()
     s_mesh = time.perf_counter() - w0
     rays = render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk)
-    stages = {"unet_iteration_ms": ms_unet, "unet_total_s": ms_unet * UNET_ITERS * 1e-3, "vae_decode4_ms": ms_dec,
+    stages = {"unet_iteration_ms": ms_unet, "unet_total_s": ms_unet * UNET_ITERS * 1e-3, "torch_gpu_unet_ms": ms_torch, "vae_decode4_ms": ms_dec,
               "volume_build_ms": ms_front, "export_mesh_s": s_mesh}
     return {"roofline": roofline, "stages": stages, "rays": rays}
 
@@ -352,13 +370,14 @@ def render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk):
     image()
     ms_img, outs = ev_time(image)
     o = outs[0]
-    # dominant kernels of the ray march, timed alone on the first chunk
+    # dominant kernels of the ray march, timed alone on the first KCHUNK rays (the slice round 1 reported)
+    KCHUNK = 8192
     vol_cl = channel_last_volume(vol)
     pack = tr.sdf_network_lod0.sdf_layer.packed()
-    mid = o['mid_z_vals'].contiguous()
-    active = (o['inside_sphere'] > 0).to(torch.uint8).reshape(-1).contiguous()
+    mid = o['mid_z_vals'][:KCHUNK].contiguous()
+    active = (o['inside_sphere'][:KCHUNK] > 0).to(torch.uint8).reshape(-1).contiguous()
     n_act = int(active.sum())
-    src = ops.PointSource.rays(ro[:CHUNK], rd[:CHUNK], mid)
+    src = ops.PointSource.rays(ro[:KCHUNK], rd[:KCHUNK], mid)
     f_sdf = lambda: ops.sdf_query(src, vol_cl, pack, active=active, want_grad=True)
     f_sdf()
     ms_sdf = float(np.mean([ev_time(f_sdf)[0] for _ in range(3)]))
@@ -380,7 +399,7 @@ def render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk):
             "workload": "65536 rays x (64+64) samples x 32 views, volume + feature maps resident; SDF MLP split-fp16 tensor cores (fp32-grade), view-blending "
                         "MLPs on tensor cores (fp16 operands, fp32 accumulate / statistics)",
             "image_ms": ms_img, "frac_of_survey_contract": t_roof * 1e3 / ms_img,
-            "kernels_first_chunk": {
+            "chunk_rays": CHUNK, "kernels_first_8192_rays": {
                 "sdf_query_kernel<grad>": {"ms": ms_sdf, "tflops": n_act * (FLOP_SDF_FWD + FLOP_SDF_BWD) / (ms_sdf * 1e-3) / 1e12,
                                            "active_samples": n_act},
                 "render_blend_tc_kernel": {"ms": ms_bl, "valid_pairs": pairs, "ms_fp32_kernel": ms_bl32,

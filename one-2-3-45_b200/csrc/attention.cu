@@ -5,7 +5,7 @@
 //
 // Head dims are 40 / 80 / 160 and sequences 16..1024 tokens: far too small per (batch, head) to fill a 128-row tcgen05
 // tile pipeline, so this kernel uses warp-level mma.sync.m16n8k16 (fp16 in, fp32 accumulate) in the FlashAttention-2
-// arrangement: one CTA = 4 warps = 64 queries of one (b, h); K / V stream through shared memory in 64-key tiles (both row-major;
+// arrangement: one CTA = 4 warps = 64 queries of one (b, h); K / V stream through a two-stage cp.async ring of 64-key tiles (both row-major;
 // the P V operand comes out of ldmatrix.trans); online softmax in fp32 registers with exp2; the S
 // accumulator fragments are re-used in place as the A fragments of the P V product.  The arithmetic is softmax-bound
 // (N^2 exps per head), not tensor-bound, at these sizes.
@@ -26,6 +26,13 @@ __device__ __forceinline__ uint32_t pack2(float x, float y) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 2^x on the SFU (ex2.approx: 2 ulp; the probabilities are rounded to fp16 for the P V product right after)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int QT = 64, KT = 64;  // queries per CTA, keys per tile
 
 template <int D, int DP>  // head dim and its padding to a multiple of 16
@@ -35,18 +42,37 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
   pdl_wait();
   pdl_trigger();
   constexpr int LDQ = DP + 8, KS = DP / 16, NO = DP / 8;
+  constexpr int STAGE = 2 * KT * LDQ;      // halves per K + V stage
   extern __shared__ __align__(16) __half smem_h[];
   __half* sQ = smem_h;
-  __half* sK = sQ + QT * LDQ;
-  __half* sV = sK + KT * LDQ;              // row-major [key][d] like K; the PV operand is read with ldmatrix.trans
+  __half* sKV = sQ + QT * LDQ;             // two stages of [K tile | V tile], both row-major [key][d]; the P V operand is read with ldmatrix.trans
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
   const int q0 = blockIdx.x * QT;
   const int64_t base = (int64_t)b * N * ld + (int64_t)h * D;
   constexpr int CH = D / 8;  // 16-byte chunks per row
 
-  for (int i = tid; i < QT * LDQ / 8; i += 128) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
+  // K / V tiles stream through a two-stage cp.async ring: tile i + 1 is in flight while tile i is multiplied (round 1 loaded
+  // each tile synchronously between two __syncthreads: the kernel sat at ~1/7 of its issue-bound time waiting for L2).
+  // Rows past N: K garbage is masked after the product; V must be finite (0 * NaN), so its copy zero-fills (src-size 0).
+  auto load_tile = [&](int stage, int k0) {
+    __half* dK = sKV + stage * STAGE;
+    __half* dV = dK + KT * LDQ;
+    for (int i = tid; i < KT * CH; i += 128) {
+      const int r = i / CH, c = i % CH;
+      const bool in = k0 + r < N;
+      const int64_t off = base + (int64_t)(in ? k0 + r : 0) * ld + 8 * c;
+      const uint32_t ak = (uint32_t)__cvta_generic_to_shared(dK + r * LDQ + 8 * c), av = (uint32_t)__cvta_generic_to_shared(dV + r * LDQ + 8 * c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ak), "l"(k + off) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(av), "l"(v + off), "r"(in ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // zero Q's and both stages' padding columns d..DP-1 (the copies only touch the first d columns), then Q
+  for (int i = tid; i < (QT * LDQ + 2 * STAGE) / 8; i += 128) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  load_tile(0, 0);
   for (int i = tid; i < QT * CH; i += 128) {
     int r = i / CH, c = i % CH;
     if (q0 + r < N) *reinterpret_cast<uint4*>(sQ + r * LDQ + 8 * c) = *reinterpret_cast<const uint4*>(q + base + (int64_t)(q0 + r) * ld + 8 * c);
@@ -66,19 +92,13 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
   for (int n = 0; n < NO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
 
-  // padding columns d..DP-1 of K and V are written once; the tile loads below only touch the first d columns
-  for (int i = tid; i < 2 * KT * LDQ / 8; i += 128) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0, 0, 0, 0);
-  for (int k0 = 0; k0 < N; k0 += KT) {
-    __syncthreads();  // previous tile fully consumed (first pass: zero fill visible)
-    for (int i = tid; i < KT * CH; i += 128) {
-      int r = i / CH, c = i % CH;
-      const bool in = k0 + r < N;
-      // rows past N: K garbage is masked after the product; V must be finite (0 * NaN), so it is zeroed
-      const int64_t off = base + (int64_t)(in ? k0 + r : 0) * ld + 8 * c;
-      *reinterpret_cast<uint4*>(sK + r * LDQ + 8 * c) = *reinterpret_cast<const uint4*>(k + off);
-      *reinterpret_cast<uint4*>(sV + r * LDQ + 8 * c) = in ? *reinterpret_cast<const uint4*>(v + off) : make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
+  int it = 0;
+  for (int k0 = 0; k0 < N; k0 += KT, ++it) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // tile `it` has landed (it is the only group in flight here)
+    __syncthreads();                                        // ... for every thread, and tile it - 1 is fully consumed
+    if (k0 + KT < N) load_tile((it + 1) & 1, k0 + KT);      // overwrites the stage tile it - 1 used
+    const __half* sK = sKV + (it & 1) * STAGE;
+    const __half* sV = sK + KT * LDQ;
     // ---- S = Q K^T for this warp's 16 queries x 64 keys
     float s[KT / 8][4];
 #pragma unroll
@@ -105,13 +125,13 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    float a0 = ex2(m0 - mn0), a1 = ex2(m1 - mn1);
     m0 = mn0, m1 = mn1;
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int j = 0; j < KT / 8; ++j) {
-      s[j][0] = exp2f(s[j][0] - mn0), s[j][1] = exp2f(s[j][1] - mn0);
-      s[j][2] = exp2f(s[j][2] - mn1), s[j][3] = exp2f(s[j][3] - mn1);
+      s[j][0] = ex2(s[j][0] - mn0), s[j][1] = ex2(s[j][1] - mn0);
+      s[j][2] = ex2(s[j][2] - mn1), s[j][3] = ex2(s[j][3] - mn1);
       r0 += s[j][0] + s[j][1], r1 += s[j][2] + s[j][3];
     }
     l0 = l0 * a0 + r0, l1 = l1 * a1 + r1;
@@ -161,10 +181,11 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
   float sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream;
   const __half *qh = (const __half*)q, *kh = (const __half*)k, *vh = (const __half*)v;
-  auto smem = [](int dp) { return (size_t)((QT + 2 * KT) * (dp + 8)) * sizeof(__half); };
+  auto smem = [](int dp) { return (size_t)((QT + 4 * KT) * (dp + 8)) * sizeof(__half); };   // Q + two stages of K and V
   static PerDeviceOnce attr;
   if (attr.need()) {
     O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(160)));
+    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<80, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(80)));
   }
   if (d == 40) O2345_CUDA(launch_pdl(attention_kernel<40, 48>, dim3(grid), dim3(128), (size_t)(smem(48)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
   else if (d == 64) O2345_CUDA(launch_pdl(attention_kernel<64, 64>, dim3(grid), dim3(128), (size_t)(smem(64)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));

@@ -8,7 +8,8 @@ import torch
 from o2345 import _lib
 from o2345.unet import UNetModel
 net = UNetModel().cuda().requires_grad_(False)
-net.fuse_gn_stats = os.environ.get("O2345_FUSE_GN", "1") != "0"
+if "O2345_FUSE_GN" in os.environ:
+    net.fuse_gn_stats = os.environ["O2345_FUSE_GN"] != "0"
 x = torch.randn(8, 8, 32, 32, device="cuda"); t = torch.full((8,), 501, device="cuda"); ctx = torch.randn(8, 1, 768, device="cuda")
 for _ in range(3):
     net(x, t, ctx)
