@@ -333,6 +333,11 @@ int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* wei
 int64_t o2345_groupnorm_scratch_floats(int B, int G);
 int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta,
                           float* scratch, float* scale, float* shift, o2345_stream_t stream);
+/* GroupNorm(x) (+SiLU if act) of a channel-last activation x [B, HW, C] -> out [B, HW, C], statistics and apply in ONE kernel:
+ * each image is handled by a thread-block cluster whose CTAs exchange their partial sums through distributed shared memory
+ * (no scratch, no global atomics).  Same result as o2345_groupnorm_stats + o2345_norm_act_im2col(ksize 1). */
+int o2345_groupnorm_apply(const void* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta, int act,
+                          void* out, o2345_stream_t stream);
 /* out [B*Ho*Wo, k*k*C] (column order ky,kx,c) = patches of f(x), f = x * scale + shift (+SiLU if act) when scale != NULL.
  * upsample != 0: nearest x2 replication of x before the convolution.  Zero padding k/2 on the high side and
  * pad_lo on the low side (pad_lo < 0: k/2; pad_lo = 0 reproduces the VAE encoder's F.pad(x, (0,1,0,1))). */

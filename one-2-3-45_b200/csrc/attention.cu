@@ -33,14 +33,17 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-constexpr int QT = 64, KT = 64;  // queries per CTA, keys per tile
+constexpr int KT = 64;  // keys per tile
 
-template <int D, int DP>  // head dim and its padding to a multiple of 16
-__global__ void __launch_bounds__(128)
+// D: head dim, DP: its padding to a multiple of 16, NW: warps per CTA = 16 queries each (8 warps share one K / V stream for
+// 128 queries: half the shared-memory fills per query of the 4-warp version, used for long sequences)
+template <int D, int DP, int NW>
+__global__ void __launch_bounds__(32 * NW)
 attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v, int N, int H, int ld,
                  __half* __restrict__ out, int ldo, float scale_log2) {
   pdl_wait();
   pdl_trigger();
+  constexpr int QT = 16 * NW, NT = 32 * NW;
   constexpr int LDQ = DP + 8, KS = DP / 16, NO = DP / 8;
   constexpr int STAGE = 2 * KT * LDQ;      // halves per K + V stage
   extern __shared__ __align__(16) __half smem_h[];
@@ -58,7 +61,7 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
   auto load_tile = [&](int stage, int k0) {
     __half* dK = sKV + stage * STAGE;
     __half* dV = dK + KT * LDQ;
-    for (int i = tid; i < KT * CH; i += 128) {
+    for (int i = tid; i < KT * CH; i += NT) {
       const int r = i / CH, c = i % CH;
       const bool in = k0 + r < N;
       const int64_t off = base + (int64_t)(in ? k0 + r : 0) * ld + 8 * c;
@@ -70,10 +73,10 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
   };
 
   // zero Q's and both stages' padding columns d..DP-1 (the copies only touch the first d columns), then Q
-  for (int i = tid; i < (QT * LDQ + 2 * STAGE) / 8; i += 128) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (QT * LDQ + 2 * STAGE) / 8; i += NT) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   load_tile(0, 0);
-  for (int i = tid; i < QT * CH; i += 128) {
+  for (int i = tid; i < QT * CH; i += NT) {
     int r = i / CH, c = i % CH;
     if (q0 + r < N) *reinterpret_cast<uint4*>(sQ + r * LDQ + 8 * c) = *reinterpret_cast<const uint4*>(q + base + (int64_t)(q0 + r) * ld + 8 * c);
   }
@@ -102,12 +105,18 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
     // ---- S = Q K^T for this warp's 16 queries x 64 keys
     float s[KT / 8][4];
 #pragma unroll
-    for (int j = 0; j < KT / 8; ++j) {
+    for (int j = 0; j < KT / 8; j += 2) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      s[j + 1][0] = s[j + 1][1] = s[j + 1][2] = s[j + 1][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
-        const __half* pk = sK + (8 * j + g) * LDQ + 16 * kk + 2 * t;
-        mma16816(s[j], qa[kk], *reinterpret_cast<const uint32_t*>(pk), *reinterpret_cast<const uint32_t*>(pk + 8));
+        // one ldmatrix.x4 = the B fragments of two MMAs: matrices (keys 8j.., d 16kk..), (8j.., 16kk+8..), (8j+8.., 16kk..),
+        // (8j+8.., 16kk+8..); lane l supplies the row address of matrix l / 8, row l % 8
+        uint32_t b0, b1, b2, b3;
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sK + (8 * j + 8 * (lane >> 4) + (lane & 7)) * LDQ + 16 * kk + 8 * ((lane >> 3) & 1));
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+        mma16816(s[j], qa[kk], b0, b1);
+        mma16816(s[j + 1], qa[kk], b2, b3);
       }
     }
     // ---- online softmax (rows g and g+8 of this warp's tile), base-2 exponent with the scale folded in
@@ -177,21 +186,35 @@ extern "C" int o2345_attention_f16(const void* q, const void* k, const void* v, 
   O2345_CHECK_ARG(B > 0 && N > 0 && H > 0 && (ld % 8) == 0 && (ldo % 2) == 0, "bad sizes");
   O2345_CHECK_ARG(d == 40 || d == 64 || d == 80 || d == 160, "head dim must be 40, 64, 80 or 160");
   O2345_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0, "q/k/v must be 16-byte aligned");
-  dim3 grid(cdiv(N, QT), B * H);
+  const int nw = N >= 512 ? 8 : 4;               // 128 queries per CTA on long sequences
+  dim3 grid(cdiv(N, 16 * nw), B * H);
   float sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = (cudaStream_t)stream;
   const __half *qh = (const __half*)q, *kh = (const __half*)k, *vh = (const __half*)v;
-  auto smem = [](int dp) { return (size_t)((QT + 4 * KT) * (dp + 8)) * sizeof(__half); };   // Q + two stages of K and V
+  auto smem = [&](int dp) { return (size_t)((16 * nw + 4 * KT) * (dp + 8)) * sizeof(__half); };   // Q + two stages of K and V
   static PerDeviceOnce attr;
   if (attr.need()) {
-    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(160)));
-    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<80, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(80)));
+    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((64 + 4 * KT) * 168 * 2)));
+    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<160, 160, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 4 * KT) * 168 * 2)));
+    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<80, 80, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((64 + 4 * KT) * 88 * 2)));
+    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<80, 80, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 4 * KT) * 88 * 2)));
+    O2345_CUDA(cudaFuncSetAttribute(attention_kernel<64, 64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((128 + 4 * KT) * 72 * 2)));
   }
-  if (d == 40) O2345_CUDA(launch_pdl(attention_kernel<40, 48>, dim3(grid), dim3(128), (size_t)(smem(48)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
-  else if (d == 64) O2345_CUDA(launch_pdl(attention_kernel<64, 64>, dim3(grid), dim3(128), (size_t)(smem(64)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
-  else if (d == 80) O2345_CUDA(launch_pdl(attention_kernel<80, 80>, dim3(grid), dim3(128), (size_t)(smem(80)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
-  else if (d == 160) O2345_CUDA(launch_pdl(attention_kernel<160, 160>, dim3(grid), dim3(128), (size_t)(smem(160)), st, qh, kh, vh, N, H, ld, (__half*)out, ldo, sl2));
+#define O2345_ATT(D_, DP_)                                                                                                        \
+  do {                                                                                                                            \
+    if (nw == 8)                                                                                                                  \
+      O2345_CUDA(launch_pdl(attention_kernel<D_, DP_, 8>, dim3(grid), dim3(256), smem(DP_), st, qh, kh, vh, N, H, ld, (__half*)out, \
+                            ldo, sl2));                                                                                           \
+    else                                                                                                                          \
+      O2345_CUDA(launch_pdl(attention_kernel<D_, DP_, 4>, dim3(grid), dim3(128), smem(DP_), st, qh, kh, vh, N, H, ld, (__half*)out, \
+                            ldo, sl2));                                                                                           \
+  } while (0)
+  if (d == 40) O2345_ATT(40, 48);
+  else if (d == 64) O2345_ATT(64, 64);
+  else if (d == 80) O2345_ATT(80, 80);
+  else if (d == 160) O2345_ATT(160, 160);
   else { set_error("o2345_attention_f16: head dim %d not built (40 / 64 / 80 / 160)", d); return O2345_EUNSUPPORTED; }
+#undef O2345_ATT
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -203,6 +203,94 @@ __global__ void norm_act_im2col_stats_kernel(const __half* __restrict__ x, int H
   }
 }
 
+// GroupNorm (+SiLU) of a whole activation in ONE kernel (ksize 1: the implicit-conv and transformer inputs, 55 of the 61 GroupNorms
+// of a UNet pass): an image is handled by one thread-block CLUSTER of CL CTAs.  Pass 1: every CTA sums its slab of pixels
+// (16-byte loads, a thread keeps its 8-channel slot) into per-group shared-memory sums; the CL partial sums are exchanged
+// through distributed shared memory (ld.shared::cluster) around one cluster barrier; pass 2: the slab is read again (L2
+// resident), normalised and written.  Replaces groupnorm_stats (global atomics + ticket + last-CTA finalize) followed by
+// norm_act_im2col: one launch instead of two, no global atomics, no scratch.
+__global__ void groupnorm_apply_cluster_kernel(const __half* __restrict__ x, int HW, int C, int G, float eps,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                               __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float gsm[];           // [2 G] this CTA's sums, then [2 G] mean / rstd
+  uint32_t rank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const int b = blockIdx.y, cg = C / G, c8n = C >> 3;
+  const int slot = threadIdx.x % c8n, prow = threadIdx.x / c8n, rows = blockDim.x / c8n;   // blockDim is a multiple of c8n
+  for (int i = threadIdx.x; i < 4 * G; i += blockDim.x) gsm[i] = 0.f;
+  __syncthreads();
+  const int P = (HW + (int)csize - 1) / (int)csize;
+  const int p0 = (int)rank * P, p1 = min(HW, p0 + P);
+  const __half* base = x + (int64_t)b * HW * C + slot * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f, q[e] = 0.f;
+  for (int pix = p0 + prow; pix < p1; pix += rows) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + (int64_t)pix * C);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      s[2 * e] += f.x, q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
+      s[2 * e + 1] += f.y, q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
+    }
+  }
+  {
+    int g = (slot * 8) / cg;
+    float rs = 0.f, rq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ge = (slot * 8 + e) / cg;
+      if (ge != g) { atomicAdd(gsm + 2 * g, rs), atomicAdd(gsm + 2 * g + 1, rq), rs = rq = 0.f, g = ge; }
+      rs += s[e], rq += q[e];
+    }
+    atomicAdd(gsm + 2 * g, rs), atomicAdd(gsm + 2 * g + 1, rq);
+  }
+  // every CTA's partial sums become visible to the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+    float t = 0.f;
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(gsm + i);
+    for (uint32_t r = 0; r < csize; ++r) {
+      uint32_t remote;
+      float v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+      t += v;
+    }
+    gsm[2 * G + i] = t;
+  }
+  __syncthreads();
+  // no CTA may leave (or overwrite its sums) while a sibling still reads them
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  float sv[8], tv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = slot * 8 + e, g = c / cg;
+    const float n = (float)HW * (float)cg, m = gsm[2 * G + 2 * g] / n;
+    const float r = rsqrtf(fmaxf(gsm[2 * G + 2 * g + 1] / n - m * m, 0.f) + eps);
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    sv[e] = r * ga, tv[e] = be - m * r * ga;
+  }
+  __half* obase = out + (int64_t)b * HW * C + slot * 8;
+  for (int pix = p0 + prow; pix < p1; pix += rows) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + (int64_t)pix * C);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    __half2 r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h[e]);
+      f.x = fmaf(f.x, sv[2 * e], tv[2 * e]), f.y = fmaf(f.y, sv[2 * e + 1], tv[2 * e + 1]);
+      if (act) f.x = silu(f.x), f.y = silu(f.y);
+      r[e] = __floats2half2_rn(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(obase + (int64_t)pix * C) = *reinterpret_cast<uint4*>(r);
+  }
+}
+
 // one warp per row: y = (x - mean) * rstd * gamma + beta, fp32 math
 __global__ void layernorm_rows_kernel(const __half* __restrict__ x, int64_t M, int C, float eps,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -442,6 +530,34 @@ extern "C" int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G,
   chunks = cdiv(HW, P);
   O2345_CUDA(launch_pdl(groupnorm_stats_kernel, dim3(dim3(chunks, B)), dim3(threads), (size_t)(4 * G * sizeof(float)), ST, (const __half*)x, HW, C, G, eps, gamma, beta,
                                                                                   scratch, B, P, scale, shift));
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+extern "C" int o2345_groupnorm_apply(const void* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta,
+                                     int act, void* out, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && out && B > 0 && HW > 0 && G > 0 && G <= 256 && C % G == 0, "bad arguments");
+  O2345_CHECK_ARG((C % 8) == 0 && C / 8 <= 1024 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0,
+                  "C must be a multiple of 8 (<= 8192), x and out 16-byte aligned");
+  const int c8n = C / 8;
+  const int rows = c8n >= 512 ? 1 : 512 / c8n;
+  const int threads = c8n * rows;
+  // CTAs per image = cluster size: enough to spread an image over 1 / B of the GPU, at most 16 (non-portable size), and no
+  // more than the image has pixel rows for
+  int cl = 16;
+  while (cl > 1 && (cl * B > 2 * sm_count() || HW < cl * rows)) cl >>= 1;
+  static PerDeviceOnce attr;
+  if (attr.need()) O2345_CUDA(cudaFuncSetAttribute(groupnorm_apply_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cl, B), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = 4 * G * sizeof(float), cfg.stream = ST;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = cl, at[1].val.clusterDim.y = 1, at[1].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 2;
+  O2345_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_apply_cluster_kernel, (const __half*)x, HW, C, G, eps, gamma, beta, act, (__half*)out));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -68,7 +68,11 @@ def main(argv=None):
         mesh = trainer(sample, mode="export_mesh", resolution=args.resolution)
         print(f"{len(mesh['vertices'])} vertices, {len(mesh['triangles'])} triangles -> {os.path.join(exp_dir, 'mesh.ply')}")
         return mesh
-    out = trainer(sample, mode="val", perturb_overwrite=0, background_rgb=1.0, alpha_inter_ratio_lod0=1.0)
+    # perturb_overwrite stays -1: the stratified jitter follows the conf's model.trainer.perturb (1.0 in the demo conf), as in
+    # the reference's validate(); white background and alpha_inter_ratio 1.0 as at iter_step 215 000 (:412-418,528-540)
+    # (512-ray chunks as in the reference: the host generator's draws -- jitter, then 1024 random points per chunk -- interleave
+    # the same way)
+    out = trainer(sample, mode="val", background_rgb=1.0, alpha_inter_ratio_lod0=1.0)
     W, H = int(sample['img_wh'][0][0]), int(sample['img_wh'][0][1])
     from PIL import Image
     Image.fromarray((np.clip(out["color"].reshape(H, W, 3), 0, 1) * 255).astype(np.uint8)).save(os.path.join(exp_dir, "val_color.png"))

@@ -90,6 +90,7 @@ _SIGS = {
     "o2345_groupnorm_scratch_floats": (c_i64, [C.c_int, C.c_int]),
     "o2345_groupnorm_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp, c_fp,
                                         c_fp]),
+    "o2345_groupnorm_apply": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp, C.c_int, c_fp, c_fp]),
     "o2345_norm_act_im2col": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp,
                                         C.c_int, c_fp, c_fp]),
     "o2345_norm_act_im2col_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int,

@@ -108,6 +108,19 @@ def groupnorm_stats(x, B, HW, C, G=32, eps=1e-5, gamma=None, beta=None):
     return scale, shift
 
 
+def groupnorm_apply_pays(B, HW, C):
+    """The one-kernel GroupNorm spreads an image over at most 16 CTAs: it wins while a CTA's slab stays small (the UNet's
+    activations: <= 123 KB); the VAE's 128-channel 256 x 256 maps keep the many-CTA statistics kernel + apply."""
+    return HW * C * 2 <= 16 * 131072
+
+
+def groupnorm_apply(x, B, HW, C, G, eps, gamma, beta, act):
+    """GroupNorm (+SiLU) of x [B*HW, C] in one cluster kernel (statistics exchanged through distributed shared memory)."""
+    out = torch.empty(B * HW, C, dtype=_f16, device=x.device)
+    L.call("o2345_groupnorm_apply", _v(x), B, HW, C, int(G), float(eps), _p(gamma, _f32), _p(beta, _f32), int(act), _v(out), _stream())
+    return out
+
+
 def norm_act_im2col(x, B, H, W, C, ksize=3, stride=1, upsample=False, gn=None, act=False, pad_lo=-1):
     """gn = (scale, shift) from groupnorm_stats or None.  Returns ([B*Ho*Wo, k*k*C] fp16, Ho, Wo)."""
     Hin, Win = (2 * H, 2 * W) if upsample else (H, W)

@@ -195,6 +195,7 @@ class UNetModel(nn.Module):
         # serialise same-address updates (~13 us per producing GEMM, more than the 46 statistics kernels it removes).
         # Kept as a tested option (tests/test_gpu_gemm.py::test_epilogue_groupnorm_statistics_feed_the_next_norm).
         self.fuse_gn_stats = False
+        self.gn_one_kernel = True    # GroupNorm statistics + apply in one cluster kernel (o2345_groupnorm_apply)
         self._arena, self._arena_off, self._arena_need = None, 0, 0
 
     # ------------------------------------------------------------------ executor
@@ -239,6 +240,8 @@ class UNetModel(nn.Module):
         if xs is not None:
             ga, be = pk.norm(gn)
             return A.norm_act_im2col_stats(x, B, H, W, C, ksize, stride, up, xs[0], xs[1], 32, gn.eps, ga, be, act)
+        if ksize == 1 and stride == 1 and not up and self.gn_one_kernel and A.groupnorm_apply_pays(B, H * W, C):
+            return A.groupnorm_apply(x, B, H * W, C, 32, gn.eps, *pk.norm(gn), act), H, W
         g = A.groupnorm_stats(x, B, H * W, C, 32, gn.eps, *pk.norm(gn))
         return A.norm_act_im2col(x, B, H, W, C, ksize, stride, up, g, act)
 

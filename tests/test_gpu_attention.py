@@ -6,7 +6,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("B,N,H,d", [(2, 1024, 8, 40), (8, 256, 8, 80), (3, 64, 8, 160), (2, 16, 8, 160), (1, 100, 2, 40)])
+@pytest.mark.parametrize("B,N,H,d", [(2, 1024, 8, 40), (8, 256, 8, 80), (3, 64, 8, 160), (2, 16, 8, 160), (1, 100, 2, 40), (1, 640, 4, 80),
+                                     (1, 1000, 2, 160), (2, 257, 16, 64), (1, 577, 3, 64)])
 def test_attention_matches_reference(B, N, H, d):
     from o2345 import ops_a
     g = torch.Generator(device="cuda").manual_seed(N + d)

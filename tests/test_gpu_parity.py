@@ -207,6 +207,44 @@ def test_render_against_oracle_same_volume(om, tr, dev, precision):
     assert float((res["gradients"].cpu()[same] - ref["gradients"][same]).abs().mean()) < 1e-4
 
 
+def test_stochastic_val_render_matches_oracle_with_the_same_jitter(om, tr, dev):
+    """`--mode val` with perturb = 1.0 (the conf default): the stratified jitter is drawn with torch.rand on the HOST generator in
+    the reference (sparse_neus_renderer.py:508-515), so seeding it reproduces the draws on both sides."""
+    n_s = tr.sdf_renderer_lod0.n_samples
+    kw = dict(background_rgb=1.0, alpha_inter_ratio=1.0, lod=0, conditional_volume=om.volume.to(dev),
+              conditional_valid_mask_volume=om.occ.to(dev), feature_maps=om.fmaps.to(dev), color_maps=om.imgs.to(dev),
+              w2cs=om.w2cs.to(dev), intrinsics=om.intr.to(dev), img_wh=[MINI["W"], MINI["H"]], query_c2w=om.qc2w.to(dev))
+    old = tr.sdf_renderer_lod0.blend_precision
+    tr.sdf_renderer_lod0.blend_precision = 0
+    try:
+        torch.manual_seed(77)
+        res = tr.sdf_renderer_lod0.render(om.rays_o.to(dev), om.rays_d.to(dev), om.near.to(dev), om.far.to(dev), tr.sdf_network_lod0,
+                                          tr.rendering_network_lod0, perturb_overwrite=1.0, **kw)
+    finally:
+        tr.sdf_renderer_lod0.blend_precision = old
+    # the oracle, fed the same jittered coarse depths
+    R = om.rays_o.shape[0]
+    z = (om.near + (om.far - om.near) * torch.linspace(0.0, 1.0, n_s)[None]).expand(R, n_s)
+    mids = .5 * (z[..., 1:] + z[..., :-1])
+    upper, lower = torch.cat([mids, z[..., -1:]], -1), torch.cat([z[..., :1], mids], -1)
+    torch.manual_seed(77)
+    z0 = lower + (upper - lower) * torch.rand(z.shape)
+    st = om.st
+    zz = O.hierarchical_z(om.rays_o, om.rays_d, om.near, om.far, om.volume, om.occ, st["sdf_network_lod0"], z_init=z0.contiguous())
+    ref = O.render_fine(om.rays_o, om.rays_d, zz, float((om.far - om.near) / n_s), om.volume, om.occ, om.fmaps, om.imgs, om.w2cs, om.intr,
+                        om.qc2w, st["sdf_network_lod0"], st["rendering_network_lod0"], st["variance_network_lod0"]["variance"],
+                        W=MINI["W"], H=MINI["H"])
+    dz = (res["z_vals"].cpu() - zz).abs().max(dim=1)[0]
+    same = dz < 1e-5
+    assert float(same.float().mean()) >= 0.5 and float(dz.max()) < 0.04
+    assert maxerr(res["color_fine"][same.to(dev)], ref["color"][same]) < 2e-4
+    assert maxerr(res["depth"][same.to(dev)], ref["depth"][same]) < 2e-4
+    assert maxerr(res["color_fine"], ref["color"]) < 5e-3
+    # and it is NOT the deterministic render: the jitter moved the samples
+    det = _render(tr, om, dev, om.volume.to(dev), om.occ.to(dev), om.fmaps.to(dev))
+    assert float((det["z_vals"] - res["z_vals"]).abs().max()) > 1e-3
+
+
 def test_render_end_to_end_against_reference_golden(om, tr, gpu, dev, golden, precision):
     res = _render(tr, om, dev, gpu["cond"]["dense_volume_scale0"], gpu["cond"]["valid_mask_volume_scale0"], gpu["fm"])
     assert maxerr(res["color_fine"], golden["color"]) < 2e-3 + BLEND_TOL[precision]

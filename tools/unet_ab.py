@@ -10,6 +10,8 @@ from o2345.unet import UNetModel
 net = UNetModel().cuda().requires_grad_(False)
 if "O2345_FUSE_GN" in os.environ:
     net.fuse_gn_stats = os.environ["O2345_FUSE_GN"] != "0"
+if "O2345_GN_ONE" in os.environ:
+    net.gn_one_kernel = os.environ["O2345_GN_ONE"] != "0"
 x = torch.randn(8, 8, 32, 32, device="cuda"); t = torch.full((8,), 501, device="cuda"); ctx = torch.randn(8, 1, 768, device="cuda")
 for _ in range(3):
     net(x, t, ctx)
