@@ -21,7 +21,7 @@ ATTN_DS = (1, 2, 4)
 def timestep_embedding(t, dim):
     """reference util.py:151-171"""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], -1)
 
