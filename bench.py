@@ -402,7 +402,7 @@ def render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk):
             "chunk_rays": CHUNK, "kernels_first_8192_rays": {
                 "sdf_query_kernel<grad>": {"ms": ms_sdf, "tflops": n_act * (FLOP_SDF_FWD + FLOP_SDF_BWD) / (ms_sdf * 1e-3) / 1e12,
                                            "active_samples": n_act},
-                "render_blend_tc_kernel": {"ms": ms_bl, "valid_pairs": pairs, "ms_fp32_kernel": ms_bl32,
+                "render_blend_tc_kernel (mma.sync, default)" if prec == 1 else "render_blend_kernel precision %d" % prec: {"ms": ms_bl, "valid_pairs": pairs, "ms_fp32_kernel": ms_bl32,
                                            "max_colour_drift_vs_fp32_kernel": drift,
                                         "gather_gbs": (pairs * 960 + n_act * 544) / (ms_bl * 1e-3) / 1e9}}}
 

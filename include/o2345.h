@@ -243,6 +243,7 @@ typedef struct o2345_views {
  * matrix stored [in][out] in the order documented in csrc/render.cu. */
 #define O2345_BLEND_FP32 0     /* fp32 FMA mat-vecs in the reference's operation order (tight oracle parity)            */
 #define O2345_BLEND_TC_FP16 1  /* per-(sample, view) MLPs as mma.sync products: fp16 operands, fp32 accumulate / statistics */
+#define O2345_BLEND_TC5 2      /* the same MLPs as tcgen05.mma M = 128 tiles (4 samples x 32 views, a lane is a view), TMEM accumulators */
 int o2345_render_blend(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl,
                        const float* occ, int D, const o2345_views* views, int dir_mode, const float* query_center,
                        const float* dirs, const float* rnet_pack, int precision, float* rgb, int32_t* nvalid,

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libo2345_sm100.so")
-SOURCES = ["api.cu", "sdf_mlp.cu", "costvol.cu", "spconv.cu", "mcubes.cu", "featnet.cu", "render.cu", "render_tc.cu", "sdf_mlp_tc.cu", "gemm_tc.cu", "unet_ops.cu", "attention.cu"]
+SOURCES = ["api.cu", "sdf_mlp.cu", "costvol.cu", "spconv.cu", "mcubes.cu", "featnet.cu", "render.cu", "render_tc.cu", "render_t5.cu", "sdf_mlp_tc.cu", "gemm_tc.cu", "unet_ops.cu", "attention.cu"]
 # no --use_fast_math: parity with the fp32 reference comes first
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -29,8 +29,9 @@ def nvcc():
 
 
 def _deps(src):
-    return [os.path.join(CSRC, src), os.path.join(CSRC, "common.cuh"),
-            os.path.join(HERE, "..", "include", "o2345.h")]
+    # every header of csrc/: an edit of sdf_common.cuh / render_pack.cuh must rebuild the objects that include them
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
+    return [os.path.join(CSRC, src), *headers, os.path.join(HERE, "..", "include", "o2345.h")]
 
 
 def _stale(target, deps):

@@ -619,6 +619,9 @@ namespace o2345 {
 int launch_render_blend_tc(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl, const float* occ, int D,
                            const o2345_views* views, int dir_mode, const float* query_center, const float* dirs,
                            const float* rnet_pack, float* rgb, int32_t* nvalid, cudaStream_t st);   // render_tc.cu
+int launch_render_blend_t5(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl, const float* occ, int D,
+                           const o2345_views* views, int dir_mode, const float* query_center, const float* dirs,
+                           const float* rnet_pack, float* rgb, int32_t* nvalid, cudaStream_t st);   // render_t5.cu
 }
 
 extern "C" int o2345_render_blend(const o2345_points* src, int64_t n, const uint8_t* active, const float* vol_cl,
@@ -629,8 +632,11 @@ extern "C" int o2345_render_blend(const o2345_points* src, int64_t n, const uint
   O2345_CHECK_ARG(src->mode == O2345_PTS_EXPLICIT || src->mode == O2345_PTS_RAYS, "explicit or ray points only");
   O2345_CHECK_ARG(views->V >= 1 && views->V <= 32 && views->maps && views->proj && views->centers, "1..32 views");
   O2345_CHECK_ARG((dir_mode == 0 && query_center) || (dir_mode == 1 && dirs), "direction source missing");
-  O2345_CHECK_ARG(precision == O2345_BLEND_FP32 || precision == O2345_BLEND_TC_FP16, "unknown precision");
+  O2345_CHECK_ARG(precision == O2345_BLEND_FP32 || precision == O2345_BLEND_TC_FP16 || precision == O2345_BLEND_TC5, "unknown precision");
   if (n == 0) return O2345_OK;
+  if (precision == O2345_BLEND_TC5)
+    return launch_render_blend_t5(src, n, active, vol_cl, occ, D, views, dir_mode, query_center, dirs, rnet_pack, rgb, nvalid,
+                                  (cudaStream_t)stream);
   if (precision == O2345_BLEND_TC_FP16)
     return launch_render_blend_tc(src, n, active, vol_cl, occ, D, views, dir_mode, query_center, dirs, rnet_pack, rgb, nvalid,
                                   (cudaStream_t)stream);
