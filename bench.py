@@ -162,6 +162,8 @@ def run_gpu(args):
         beat("warm-up step %d: %.2f s" % (i, time.perf_counter() - w))
     torch.cuda.synchronize()
     pk = peaks()
+    # the host-side baseline must be finished before anything else is measured (its 32 threads slow this process's launches)
+    cpu = cpu_job.join() if cpu_job is not None else None
     extras = stage_breakdown(z123, tr, dev, pk, world)
     # every rank renders its own image at the same time: the job's ray throughput is the per-rank rate of the slowest
     # rank times the number of ranks
@@ -169,7 +171,6 @@ def run_gpu(args):
     extras["rays"]["image_ms"] = img_ms
     extras["rays"]["value"] = world * N_RAYS / (img_ms * 1e-3) / 1e6
     extras["rays"]["n_gpus"] = world
-    cpu = cpu_job.join() if cpu_job is not None else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -324,13 +325,20 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
     ms_dec = float(np.mean([ev_time(lambda: vae.decode(z))[0] for _ in range(3)]))
     flops = 8 * UNET_FLOP_PER_SAMPLE
     tf = flops_counted / (ms_gemm * 1e-3) / 1e12
-    roofline = {"kernel": "gemm2_f16_tc_kernel (tcgen05.mma.cta_group::2 kind::f16; all %d GEMM / implicit-conv launches of one "
-                          "UNet iteration at batch 8)" % n_gemm,
+    # DRAM traffic of the same launches: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 165 GEMM launches of one
+    # eager UNet forward (profiles/r2_unet_launches_summary.txt), divided by the launch count -- a committed measurement, not
+    # taken live (ncu cannot run inside the bench)
+    GEMM_DRAM_BYTES_PER_ITERATION = 2620.6e6
+    roofline = {"kernel": "gemm_tc_kernel<BN, STAGES, CTAS, MODE> (tcgen05.mma kind::f16, cta_group::2 pairs; all %d GEMM / implicit-conv "
+                          "launches of one UNet iteration at batch 8)" % n_gemm,
                 "bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
-                "traffic": None, "flops_per_step": flops_counted, "gemm_ms_per_unet_iteration": ms_gemm,
+                "traffic": GEMM_DRAM_BYTES_PER_ITERATION / max(n_gemm, 1), "traffic_unit": "bytes of DRAM traffic per launch (mean)",
+                "traffic_note": "ncu: 2620.6 MB over the 165 launches of one UNet iteration; algorithmic: 1.72 GB of fp16 weights + "
+                                "~0.5 GB of activations",
+                "flops_per_step": flops_counted, "gemm_ms_per_unet_iteration": ms_gemm,
                 "note": "algorithmic FLOPs = sum of 2 M N K over the recorded launches (%.1f GFLOP; SURVEY.md 8(d) row A2 quotes "
                         "%.1f GFLOP for the same pass including attention) / CUDA-event time of those launches replayed back to back "
-                        "in one CUDA graph (split-K finalize kernels included)" % (flops_counted / 1e9, flops / 1e9)}
+                        "in one CUDA graph (split-K reductions are inside the kernel)" % (flops_counted / 1e9, flops / 1e9)}
     # ---- reconstruction stages + volume rendering
     beat("stage breakdown: reconstruction + volume rendering")
     sample = synthetic_sample(dev, n_views=N_VIEWS, H=H, W=W)

@@ -20,11 +20,23 @@ import struct
 import numpy as np
 
 
-def merge_vertices(vertices, triangles, colors=None, digits=8):
-    v = np.asarray(vertices, np.float64)
-    f = np.asarray(triangles, np.int64).reshape(-1, 3)
+def merge_vertices(vertices, triangles, colors=None, digits=8, candidates=None):
+    """candidates (optional): indices of the only vertices that can coincide with another one (marching cubes: those on a
+    lattice point).  With fewer than two of them, or no coinciding pair among them, the arrays are returned untouched; the
+    sort over all vertices is only paid when something really merges."""
+    v = np.asarray(vertices)
+    f = np.asarray(triangles)
     if len(v) == 0 or len(f) == 0:
         return v, f, colors
+    if candidates is not None:
+        cand = np.asarray(candidates, np.int64)
+        if cand.size < 2:
+            return v, f, colors
+        ck = np.round(np.asarray(v[cand], np.float64) * 10.0 ** digits).astype(np.int64)
+        if len(np.unique(ck, axis=0)) == len(ck):
+            return v, f, colors
+    v = np.asarray(v, np.float64)
+    f = np.asarray(f, np.int64).reshape(-1, 3)
     key = np.round(v * 10.0 ** digits).astype(np.int64)
     _, first, inverse = np.unique(key, axis=0, return_index=True, return_inverse=True)
     inverse = np.asarray(inverse).reshape(-1)

@@ -189,8 +189,9 @@ class SparseNeuSRenderer(nn.Module):
         verts, tris, cases = ops.marching_cubes(u, float(threshold))
         self._last_cases = cases
         # marching cubes emits one vertex per sign-changing lattice edge: two vertices can only coincide at a lattice point.
-        # How many lie within 1e-4 voxels of one tells the mesh tail whether trimesh's vertex merge could change anything.
-        self.mc_vertices_on_lattice = int(((verts - verts.round()).abs().amax(dim=1) < 1e-4).sum()) if verts.numel() else 0
+        # Those within 1e-4 voxels of one are the only candidates of trimesh's vertex merge in the mesh tail.
+        self.mc_lattice_candidates = (torch.nonzero((verts - verts.round()).abs().amax(dim=1) < 1e-4)[:, 0].cpu().numpy()
+                                      if verts.numel() else np.zeros(0, np.int64))
         b_max = np.asarray([float(v) for v in bound_max])
         b_min = np.asarray([float(v) for v in bound_min])
         vertices = verts.cpu().numpy() / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]

@@ -132,10 +132,10 @@ class GenericTrainer(nn.Module):
             vertices = (vh @ tm.T)[:, :3]
         colors = (rgb.cpu() * 255).numpy().astype(np.uint8)
         # trimesh.Trimesh(vertices, triangles, vertex_colors=...) with its default process=True merges coincident vertices
-        # before the export (reference :1374-1380).  Marching-cubes vertices can only coincide on lattice points; the
-        # renderer counted how many sit on one (on the device): fewer than two -> nothing to merge, arrays untouched.
-        if getattr(self.sdf_renderer_lod0, "mc_vertices_on_lattice", 2) >= 2:
-            vertices, triangles, colors = merge_vertices(vertices, triangles, colors)
+        # before the export (reference :1374-1380).  Marching-cubes vertices can only coincide on lattice points: the renderer
+        # listed the vertices that sit on one (on the device), and only those are compared.
+        vertices, triangles, colors = merge_vertices(vertices, triangles, colors,
+                                                     candidates=getattr(self.sdf_renderer_lod0, "mc_lattice_candidates", None))
         if self.base_exp_dir is not None:
             os.makedirs(self.base_exp_dir, exist_ok=True)
             write_ply(os.path.join(self.base_exp_dir, 'mesh.ply'), vertices, triangles, colors)
