@@ -257,7 +257,9 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
     t = torch.full((8,), 501, device=dev)
     ctx = torch.randn(8, 1, 768, device=dev)
     unet(x, t, ctx)
-    ms_unet = float(np.mean([ev_time(lambda: unet(x, t, ctx))[0] for _ in range(10)]))
+    # 20 calls queued behind each other, as the sampler issues them (a call timed alone on an idle GPU would include its
+    # own host-side launch latency, which the sampler hides behind the previous iteration)
+    ms_unet = ev_time(lambda: [unet(x, t, ctx) for _ in range(20)])[0] / 20.0
     # Device time of the tensor-core kernel inside one UNet pass: every GEMM / implicit-conv call of an eager pass is
     # recorded (operands kept alive) and replayed back to back inside ONE CUDA graph, timed with events around the
     # replay -- the kernel's launches exactly as the captured UNet graph issues them, without the glue kernels between.
