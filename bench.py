@@ -3,8 +3,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Headline metric (BASELINE.json, configs[1]): "sec/mesh end-to-end (256x256 in)".  One step = one 256x256 input
-image -> Zero123 stage 1 + stage 2 (10 DDIM sampler calls = 2x76 + 8x49 = 544 UNet iterations at the CFG batch
-of 8, fp16 tensor-core GEMMs with fp32 accumulate; 10 CLIP ViT-L/14 image embeddings, 10 VAE encodes, 40 VAE decodes)
+image -> Zero123 stage 1 + stage 2 (the reference's 10 DDIM sampler calls = 2x76 + 8x49 = 544 UNet passes over a CFG
+batch of 8, run here as the two batched calls they collapse to when the elevation is given: 76 iterations at batch 16 + 49
+at batch 64, same views, same noise per view; fp16 tensor-core GEMMs with fp32 accumulate; 9 CLIP ViT-L/14 image embeddings,
+9 VAE encodes, 40 VAE decodes)
 -> 32 views -> FeatureNet ->
 96^3 cost volume -> sparse U-Net -> 256^3 SDF grid -> marching cubes -> vertex colours -> mesh arrays on the host
 (`o2345.pipeline.image_to_mesh`).  Not inside the step (out of scope): SAM / rembg
@@ -39,8 +41,10 @@ VOL = 96
 N_RAYS = H * W
 CHUNK = 65536   # rays marched per launch group (the reference uses 512; results are per-ray, the chunk only sets the launch count)
 MESH_RES = 256
-UNET_ITERS = 2 * 76 + 8 * 49
-CONFIG = {"workload": "configs[1]: single 256x256 image -> mesh: Zero123 75/50-step DDIM fp16 (544 UNet iterations at batch 8) "
+UNET_ITERS = 2 * 76 + 8 * 49             # the reference's sampler calls: UNet passes at batch 8 (what the CPU arm extrapolates with)
+UNET_SCHEDULE = ((16, 76), (64, 49))     # (batch = views x CFG, iterations): stage 1 (8 views), stage 2 (32 views)
+CONFIG = {"workload": "configs[1]: single 256x256 image -> mesh: Zero123 75/50-step DDIM fp16 (the reference's 2x76 + 8x49 UNet passes "
+                      "at batch 8 = 4352 sample-iterations, batched as 76 iterations at batch 16 + 49 at batch 64) "
                       "+ 96^3 cost volume + 256^3 SDF grid + marching cubes, 1 image per GPU",
           "views": N_VIEWS, "vol_dim": VOL, "mesh_resolution": MESH_RES, "ddim_steps": [75, 50], "cfg_scale": 3.0,
           "l2": "inputs larger than L2 (1.72 GB fp16 UNet weights stream every iteration; 470 MB feature maps)",
@@ -51,6 +55,9 @@ UNET_FLOP_PER_SAMPLE = 176.3e9
 FLOP_SDF_FWD = 2 * 41856.0
 FLOP_SDF_BWD = 2 * (128 * 144 + 128 * 39)
 RAY_FLOP, RAY_GATHER_BYTES = 211e6, 4.0e6
+# ncu dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one eager UNet forward, by batch (profiles/)
+GEMM_DRAM_BYTES_PER_ITERATION = {8: 2620.6e6}
+GEMM_DRAM_NOTE = "ncu launch list of one UNet iteration (profiles/r2_unet_launches_summary.txt); algorithmic: 1.72 GB of fp16 weights + activations"
 PUBLISHED_SEC_PER_MESH = 40.0   # BASELINE.md section 1 (reference README.md:154, A6000, whole run.py)
 
 
@@ -249,64 +256,73 @@ class CpuBaselineJob:
 def stage_breakdown(z123, tr, dev, pk, world=1):
     """Per-stage device times, the tensor-core roofline of the dominant kernel (the tcgen05 GEMM inside the UNet)
     and the volume-rendering throughput with its own roofline.  Untimed extras; every rank runs them (symmetric)."""
-    beat("stage breakdown: UNet iteration")
+    beat("stage breakdown: UNet iterations")
     from o2345 import ops_a
     from o2345.pipeline import synthetic_sample
     unet, vae = z123.model.diffusion_model, z123.first_stage_model
-    x = torch.randn(8, 8, 32, 32, device=dev)
-    t = torch.full((8,), 501, device=dev)
-    ctx = torch.randn(8, 1, 768, device=dev)
-    unet(x, t, ctx)
-    # 20 calls queued behind each other, as the sampler issues them (a call timed alone on an idle GPU would include its
-    # own host-side launch latency, which the sampler hides behind the previous iteration)
-    ms_unet = ev_time(lambda: [unet(x, t, ctx) for _ in range(20)])[0] / 20.0
-    # Device time of the tensor-core kernel inside one UNet pass: every GEMM / implicit-conv call of an eager pass is
-    # recorded (operands kept alive) and replayed back to back inside ONE CUDA graph, timed with events around the
-    # replay -- the kernel's launches exactly as the captured UNet graph issues them, without the glue kernels between.
-    rec = []
-    real = {n: getattr(ops_a, n) for n in ("gemm", "bgemm", "conv3x3")}
 
-    def spy(name):
-        def wrap(*a, **k):
-            rec.append((name, a, k))
-            return real[name](*a, **k)
-        return wrap
-    for n in real:
-        setattr(ops_a, n, spy(n))
-    unet.use_cuda_graph = False
-    try:
+    def unet_profile(B):
+        """(ms per iteration in the captured graph, ms of its GEMM launches alone, their FLOPs, their count, inputs)."""
+        x = torch.randn(B, 8, 32, 32, device=dev)
+        t = torch.full((B,), 501, device=dev)
+        ctx = torch.randn(B, 1, 768, device=dev)
         unet(x, t, ctx)
-        torch.cuda.synchronize()
-    finally:
+        # 10 calls queued behind each other, as the sampler issues them (a call timed alone on an idle GPU would include
+        # its own host-side launch latency, which the sampler hides behind the previous iteration)
+        ms_unet = ev_time(lambda: [unet(x, t, ctx) for _ in range(10)])[0] / 10.0
+        # Device time of the tensor-core kernel inside one UNet pass: every GEMM / implicit-conv call of an eager pass is
+        # recorded (operands kept alive) and replayed back to back inside ONE CUDA graph, timed with events around the
+        # replay -- the kernel's launches exactly as the captured UNet graph issues them, without the glue kernels between.
+        rec = []
+        real = {n: getattr(ops_a, n) for n in ("gemm", "bgemm", "conv3x3")}
+
+        def spy(name):
+            def wrap(*a, **k):
+                rec.append((name, a, k))
+                return real[name](*a, **k)
+            return wrap
         for n in real:
-            setattr(ops_a, n, real[n])
-        unet.use_cuda_graph = True
-    flops_counted = 0.0
-    for name, a, k in rec:
-        if name == "gemm":
-            flops_counted += 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
-        elif name == "conv3x3":
-            flops_counted += 2.0 * a[1] * a[2] * a[3] * 9 * a[4] * a[5].shape[0]
-        else:
-            flops_counted += 2.0 * a[3] * a[4] * a[8] * a[9] * a[10]
-    side = torch.cuda.Stream()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
+            setattr(ops_a, n, spy(n))
+        unet.use_cuda_graph = False
+        try:
+            unet(x, t, ctx)
+            torch.cuda.synchronize()
+        finally:
+            for n in real:
+                setattr(ops_a, n, real[n])
+            unet.use_cuda_graph = True
+        flops_counted = 0.0
         for name, a, k in rec:
-            real[name](*a, **k)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph, stream=side):
+            if name == "gemm":
+                flops_counted += 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
+            elif name == "conv3x3":
+                flops_counted += 2.0 * a[1] * a[2] * a[3] * 9 * a[4] * a[5].shape[0]
+            else:
+                flops_counted += 2.0 * a[3] * a[4] * a[8] * a[9] * a[10]
+        side = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
             for name, a, k in rec:
                 real[name](*a, **k)
-    graph.replay()
-    torch.cuda.synchronize()
-    ms_gemm = float(np.median([ev_time(graph.replay)[0] for _ in range(10)]))
-    n_gemm = len(rec)
-    del graph
-    beat("stage breakdown: %d GEMM launches of one UNet iteration replay in %.3f ms" % (n_gemm, ms_gemm))
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for name, a, k in rec:
+                    real[name](*a, **k)
+        graph.replay()
+        torch.cuda.synchronize()
+        ms_gemm = float(np.median([ev_time(graph.replay)[0] for _ in range(10)]))
+        n = len(rec)
+        del graph, rec
+        beat("stage breakdown: UNet iteration at batch %d: %.3f ms; its %d GEMM launches replay in %.3f ms (%.0f TFLOP/s)"
+             % (B, ms_unet, n, ms_gemm, flops_counted / ms_gemm / 1e9))
+        return ms_unet, ms_gemm, flops_counted, n, (x, t, ctx)
+
+    prof = {B: unet_profile(B) for B, _ in UNET_SCHEDULE}
+    B_TOP = max(UNET_SCHEDULE, key=lambda bi: prof[bi[0]][0] * bi[1])[0]       # the batch whose iterations take the larger share
+    ms_unet, ms_gemm, flops_counted, n_gemm, (x, t, ctx) = prof[B_TOP]
     # informational (SURVEY.md 2a "beats PyTorch / cuDNN on the same box"): the plain-PyTorch restatement of the same UNet
     # (oracle/ldm_oracle.py: F.conv2d / F.linear / einsum attention -> cuDNN + cuBLAS) under fp16 autocast on this GPU, eager,
-    # outside every timed region.  It is the reference's execution model, not the product path.
+    # outside every timed region, at the same batch.  It is the reference's execution model, not the product path.
     ms_torch = None
     if int(os.environ.get("RANK", 0)) == 0:
         try:
@@ -319,25 +335,26 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
                 ms_torch = float(np.median([ev_time(lambda: LO.unet_forward(sd_t, x, t, ctx))[0] for _ in range(5)]))
             del sd_t
             torch.cuda.empty_cache()
-            beat("stage breakdown: plain PyTorch (cuDNN / cuBLAS, fp16 autocast, eager) UNet iteration %.2f ms" % ms_torch)
+            beat("stage breakdown: plain PyTorch (cuDNN / cuBLAS, fp16 autocast, eager) UNet iteration at batch %d: %.2f ms" % (B_TOP, ms_torch))
         except Exception as e:
             beat("stage breakdown: plain-PyTorch UNet timing skipped: %r" % (e,))
     z = torch.randn(4, 4, 32, 32, device=dev)
     vae.decode(z)
     ms_dec = float(np.mean([ev_time(lambda: vae.decode(z))[0] for _ in range(3)]))
-    flops = 8 * UNET_FLOP_PER_SAMPLE
+    flops = B_TOP * UNET_FLOP_PER_SAMPLE
     tf = flops_counted / (ms_gemm * 1e-3) / 1e12
-    # DRAM traffic of the same launches: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 165 GEMM launches of one
-    # eager UNet forward (profiles/r2_unet_launches_summary.txt), divided by the launch count -- a committed measurement, not
-    # taken live (ncu cannot run inside the bench)
-    GEMM_DRAM_BYTES_PER_ITERATION = 2620.6e6
+    # DRAM traffic of the same launches: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one
+    # eager UNet forward at this batch (profiles/r2_unet_b64_launches_summary.txt), divided by the launch count -- a committed
+    # measurement, not taken live (ncu cannot run inside the bench)
     roofline = {"kernel": "gemm_tc_kernel<BN, STAGES, CTAS, MODE> (tcgen05.mma kind::f16, cta_group::2 pairs; all %d GEMM / implicit-conv "
-                          "launches of one UNet iteration at batch 8)" % n_gemm,
+                          "launches of one UNet iteration at batch %d, the batch of the 49 stage-2 iterations)" % (n_gemm, B_TOP),
                 "bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
-                "traffic": GEMM_DRAM_BYTES_PER_ITERATION / max(n_gemm, 1), "traffic_unit": "bytes of DRAM traffic per launch (mean)",
-                "traffic_note": "ncu: 2620.6 MB over the 165 launches of one UNet iteration; algorithmic: 1.72 GB of fp16 weights + "
-                                "~0.5 GB of activations",
+                "traffic": GEMM_DRAM_BYTES_PER_ITERATION.get(B_TOP, 0.0) / max(n_gemm, 1) or None,
+                "traffic_unit": "bytes of DRAM traffic per launch (mean)",
+                "traffic_note": GEMM_DRAM_NOTE,
                 "flops_per_step": flops_counted, "gemm_ms_per_unet_iteration": ms_gemm,
+                "other_batches": {str(B): {"unet_iteration_ms": prof[B][0], "gemm_ms": prof[B][1],
+                                           "tflops": prof[B][2] / (prof[B][1] * 1e-3) / 1e12} for B, _ in UNET_SCHEDULE if B != B_TOP},
                 "note": "algorithmic FLOPs = sum of 2 M N K over the recorded launches (%.1f GFLOP; SURVEY.md 8(d) row A2 quotes "
                         "%.1f GFLOP for the same pass including attention) / CUDA-event time of those launches replayed back to back "
                         "in one CUDA graph (split-K reductions are inside the kernel)" % (flops_counted / 1e9, flops / 1e9)}
@@ -354,7 +371,9 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
     torch.cuda.synchronize()
     s_mesh = time.perf_counter() - w0
     rays = render_throughput(tr, sample, imgs, fmaps, cond, sizeW, sizeH, dev, pk)
-    stages = {"unet_iteration_ms": ms_unet, "unet_total_s": ms_unet * UNET_ITERS * 1e-3, "torch_gpu_unet_ms": ms_torch, "vae_decode4_ms": ms_dec,
+    stages = {"unet_iteration_ms": {"batch%d" % B: prof[B][0] for B, _ in UNET_SCHEDULE},
+              "unet_total_s": sum(prof[B][0] * n for B, n in UNET_SCHEDULE) * 1e-3,
+              "torch_gpu_unet_ms": ms_torch, "torch_gpu_unet_batch": B_TOP, "vae_decode4_ms": ms_dec,
               "volume_build_ms": ms_front, "export_mesh_s": s_mesh}
     return {"roofline": roofline, "stages": stages, "rays": rays}
 

@@ -7,7 +7,10 @@ unconditional_guidance_scale, unconditional_conditioning)` -> `(samples, {'x_int
 exactly as the reference requires; the alpha / sigma tables are read from it the way ddim.py:40-66 does
 (so an fp16-rounded schedule of a `.half()` model is inherited).  Quirks kept: the uniform
 schedule has S+1 or S+2 entries and `t_start=-1` drops the last one (76 / 49 iterations for S = 75 / 50).
-Noise comes from torch's global generator in the reference's order: x_T first, then one randn per step.
+Noise comes from torch's global generator in the reference's order: x_T first, then one randn per step.  One addition to
+the reference's signature: `step_noise` (a sequence of tensors, one per iteration) replaces those per-step draws, which is
+how several sampler calls of the reference run as ONE batched call here with the numbers each of them would have drawn
+(zero123.generate_views).
 """
 from __future__ import annotations
 
@@ -48,7 +51,7 @@ class DDIMSampler(object):
     def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
                quantize_x0=False, eta=0., mask=None, x0=None, temperature=1., noise_dropout=0., score_corrector=None,
                corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.,
-               unconditional_conditioning=None, dynamic_threshold=None, **kwargs):
+               unconditional_conditioning=None, dynamic_threshold=None, step_noise=None, **kwargs):
         if mask is not None or quantize_x0 or score_corrector is not None or noise_dropout > 0 or dynamic_threshold is not None:
             raise NotImplementedError("inpainting masks / quantisation / score correctors are not used by Zero123")
         self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
@@ -56,11 +59,11 @@ class DDIMSampler(object):
         return self.ddim_sampling(conditioning, (batch_size, C, H, W), x_T=x_T, callback=callback, img_callback=img_callback,
                                   log_every_t=log_every_t, temperature=temperature,
                                   unconditional_guidance_scale=unconditional_guidance_scale,
-                                  unconditional_conditioning=unconditional_conditioning)
+                                  unconditional_conditioning=unconditional_conditioning, step_noise=step_noise)
 
     @torch.no_grad()
     def ddim_sampling(self, cond, shape, x_T=None, callback=None, img_callback=None, log_every_t=100, temperature=1.,
-                      unconditional_guidance_scale=1., unconditional_conditioning=None, t_start=-1, **kwargs):
+                      unconditional_guidance_scale=1., unconditional_conditioning=None, t_start=-1, step_noise=None, **kwargs):
         device = self.model.betas.device
         b = shape[0]
         img = torch.randn(shape, device=device) if x_T is None else x_T
@@ -68,12 +71,15 @@ class DDIMSampler(object):
         timesteps = self.ddim_timesteps[:t_start]
         intermediates = {'x_inter': [img], 'pred_x0': [img]}
         total_steps = timesteps.shape[0]
+        if step_noise is not None and len(step_noise) != total_steps:
+            raise ValueError("step_noise holds %d tensors, the schedule has %d iterations" % (len(step_noise), total_steps))
         for i, step in enumerate(np.flip(timesteps)):
             index = total_steps - i - 1
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
             img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, temperature=temperature,
                                               unconditional_guidance_scale=unconditional_guidance_scale,
-                                              unconditional_conditioning=unconditional_conditioning)
+                                              unconditional_conditioning=unconditional_conditioning,
+                                              noise=None if step_noise is None else step_noise[i])
             if callback:
                 img = callback(i, img, pred_x0)
             if img_callback:
@@ -85,7 +91,7 @@ class DDIMSampler(object):
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, temperature=1., unconditional_guidance_scale=1.,
-                      unconditional_conditioning=None, **kwargs):
+                      unconditional_conditioning=None, noise=None, **kwargs):
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
             e = self.model.apply_model(x, t, c)
             e2 = torch.cat([e, e]).float().contiguous()          # scale * (e - e) = 0: same formula, one kernel
@@ -107,7 +113,13 @@ class DDIMSampler(object):
                 self._cin = (c, unconditional_conditioning, c_in)
             e2 = self.model.apply_model(x_in, t_in, c_in).float().contiguous()
             scale = unconditional_guidance_scale
-        noise = torch.randn(x.shape, device=x.device) * temperature     # noise_like(), reference util.py:264-267
+        if noise is None:
+            noise = torch.randn(x.shape, device=x.device)                # noise_like(), reference util.py:264-267
+        elif tuple(noise.shape) != tuple(x.shape):
+            raise ValueError("step noise of shape %s for a state of shape %s" % (tuple(noise.shape), tuple(x.shape)))
+        noise = noise.float().contiguous()
+        if temperature != 1.:
+            noise = noise * temperature
         return A.cfg_ddim_update(x.float().contiguous(), e2, noise, scale, float(self.ddim_alphas[index]),
                                  float(self.ddim_alphas_prev[index]), float(self.ddim_sigmas[index]),
                                  float(self.ddim_sqrt_one_minus_alphas[index]))

@@ -136,13 +136,13 @@ def sample_from_views(stage1, stage2, pose, device, pin=False):
 
 @torch.no_grad()
 def image_to_mesh(zero123, trainer, input_u8, polar_angle=60, resolution=256, ddim_steps=75, stage2_steps=50, scale=3.0,
-                  exp_dir=None):
+                  exp_dir=None, batched=True):
     """`python run.py --img_path X --half_precision` without SAM / elevation estimation: Zero123 stage 1 + stage 2
-    (10 DDIM sampler calls), camera set-up, cost volume, SDF grid, marching cubes, vertex colours.
+    (the reference's 10 DDIM sampler calls, run as two batched ones unless batched=False), camera set-up, cost volume, SDF grid, marching cubes, vertex colours.
     Returns dict(vertices, triangles, colors) as host numpy arrays (and writes mesh.ply when exp_dir is given)."""
     from .zero123 import generate_views
     dev = next(trainer.parameters()).device
-    stage1, stage2, pose = generate_views(zero123, input_u8, polar_angle, ddim_steps, stage2_steps, scale, exp_dir, dev)
+    stage1, stage2, pose = generate_views(zero123, input_u8, polar_angle, ddim_steps, stage2_steps, scale, exp_dir, dev, batched=batched)
     sample = sample_from_views(stage1, stage2, pose, dev)
     trainer.base_exp_dir = exp_dir
     return trainer(sample, mode="export_mesh", resolution=resolution)

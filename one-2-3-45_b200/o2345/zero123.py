@@ -24,7 +24,7 @@ import torch.nn as nn
 from . import ops_a as A
 from . import synthetic as S
 from .autoencoder import AutoencoderKL
-from .ddim import DDIMSampler
+from .ddim import DDIMSampler, make_ddim_timesteps
 from .unet import UNetModel
 
 
@@ -86,7 +86,7 @@ class LatentDiffusion(nn.Module):
     def get_learned_conditioning(self, c):
         if self.cond_stage_model is None:
             g = torch.Generator().manual_seed(7)            # no conditioning encoder attached: a fixed embedding
-            return torch.randn(c.shape[0], 1, 768, generator=g).to(c.device)
+            return torch.randn(1, 1, 768, generator=g).expand(c.shape[0], -1, -1).contiguous().to(c.device)
         enc = getattr(self.cond_stage_model, "encode", None)   # reference ddpm.py:619-626
         return enc(c) if callable(enc) else self.cond_stage_model(c)
 
@@ -107,22 +107,33 @@ class LatentDiffusion(nn.Module):
 
 @torch.no_grad()
 def sample_model_batch(model, sampler, input_im, xs, ys, n_samples=4, precision='autocast', ddim_eta=1.0, ddim_steps=75,
-                       scale=3.0, h=256, w=256):
-    """reference utils/zero123_utils.py:60-98; returns images in [0,1], float32, on the host."""
+                       scale=3.0, h=256, w=256, x_T=None, step_noise=None, decode_chunk=4):
+    """reference utils/zero123_utils.py:60-98; returns images in [0,1], float32, on the host.
+
+    Beyond the reference: `input_im` may hold G conditioning images; then n_samples views are sampled for EACH of them in
+    one batch of G * n_samples (xs / ys list the G * n_samples relative poses, image-major), which is G reference calls
+    run as one; `x_T` / `step_noise` carry the noise those calls would have drawn (see generate_views)."""
     with model.ema_scope():
-        c = model.get_learned_conditioning(input_im).tile(n_samples, 1, 1)
+        G = input_im.shape[0]
+        total = G * n_samples
+        assert len(xs) == total and len(ys) == total, "one relative pose per sampled view"
+        c = model.get_learned_conditioning(input_im)
+        c = c.tile(n_samples, 1, 1) if G == 1 else c.repeat_interleave(n_samples, 0)
         T = [[np.radians(x), np.sin(np.radians(y)), np.cos(np.radians(y)), 0] for x, y in zip(xs, ys)]
         T = torch.tensor(np.array(T))[:, None, :].float().to(c.device)
         c = model.project_condition(torch.cat([c, T], dim=-1))
+        z = model.encode_first_stage(input_im).mode().detach()
         cond = {'c_crossattn': [c],
-                'c_concat': [model.encode_first_stage(input_im).mode().detach().repeat(n_samples, 1, 1, 1)]}
+                'c_concat': [z.repeat(n_samples, 1, 1, 1) if G == 1 else z.repeat_interleave(n_samples, 0)]}
         uc = None
         if scale != 1.0:
-            uc = {'c_concat': [torch.zeros(n_samples, 4, h // 8, w // 8).to(c.device)], 'c_crossattn': [torch.zeros_like(c)]}
-        samples, _ = sampler.sample(S=ddim_steps, conditioning=cond, batch_size=n_samples, shape=[4, h // 8, w // 8],
+            uc = {'c_concat': [torch.zeros(total, 4, h // 8, w // 8).to(c.device)], 'c_crossattn': [torch.zeros_like(c)]}
+        samples, _ = sampler.sample(S=ddim_steps, conditioning=cond, batch_size=total, shape=[4, h // 8, w // 8],
                                     verbose=False, unconditional_guidance_scale=scale, unconditional_conditioning=uc,
-                                    eta=ddim_eta, x_T=None)
-        x = model.decode_first_stage(samples)
+                                    eta=ddim_eta, x_T=x_T, step_noise=step_noise)
+        # decoded n at a time, as the reference's calls decode them (the up-sampling convolutions gather patches:
+        # 0.3 GB of scratch per image)
+        x = torch.cat([model.decode_first_stage(samples[i:i + decode_chunk]) for i in range(0, total, decode_chunk)])
         return torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0).cpu()
 
 
@@ -143,36 +154,69 @@ def _as_input(u8, whiten):
     return torch.from_numpy(a / 255.0).permute(2, 0, 1)[None] * 2 - 1
 
 
+def ddim_iterations(ddim_steps, num_timesteps=1000):
+    """UNet iterations of one sampler call: the uniform schedule minus its last entry (76 / 49 for S = 75 / 50)."""
+    return len(make_ddim_timesteps(ddim_steps, num_timesteps)) - 1
+
+
 @torch.no_grad()
-def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=50, scale=3.0, exp_dir=None, device="cuda"):
-    """run.py's stage1_run + stage2_run (reference run.py:18-54) with the elevation given instead of estimated:
-    10 sampler calls = 2 x 76 + 8 x 49 UNet iterations at batch 8.  Returns (stage1 dict id -> uint8 image,
-    stage2 dict 'i_j' -> uint8 image, pose dict).  With exp_dir the same PNG files and pose.json are written."""
+def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=50, scale=3.0, exp_dir=None, device="cuda",
+                   batched=True):
+    """run.py's stage1_run + stage2_run (reference run.py:18-54) with the elevation given instead of estimated: the
+    reference's 10 sampler calls (2 x 76 + 8 x 49 UNet iterations at batch 8 = 4 views x CFG).  Returns (stage1 dict
+    id -> uint8 image, stage2 dict 'i_j' -> uint8 image, pose dict).  With exp_dir the same PNG files and pose.json are
+    written.
+
+    batched=True (default): with the elevation known the two stage-1 calls are independent of each other, and so are the
+    eight stage-2 calls once their stage-1 view exists, so they run as TWO sampler calls -- 76 iterations at batch 16
+    (8 views x CFG) and 49 iterations at batch 64 (32 views x CFG): the same 40 views and the same arithmetic per view,
+    but every weight is streamed from HBM 125 times instead of 544 and the GEMMs have 2x / 8x the rows.  The noise is
+    drawn FIRST, call by call in the reference's order and shapes (x_T, then one tensor per iteration), so every view
+    sees exactly the numbers it would have seen in the sequential run.  batched=False runs the ten calls one after the
+    other, as the reference does."""
     dev = torch.device(device)
     inp = _as_input(input_u8, False).to(dev)
     stage1, stage2 = {}, {}
+    first = list(range(4))
+    second = list(range(4, 8)) if polar_angle <= 75 else list(range(8, 12))
+    pose = S.pose_json(float(polar_angle))
 
-    def stage1_call(adjust):
+    def stage1_call(adjust, x_T=None, step_noise=None):
         sampler = DDIMSampler(model)
         imgs = sample_model_batch(model, sampler, inp, [DELTA_X_1_8[i] for i in adjust], [DELTA_Y_1_8[i] for i in adjust],
-                                  n_samples=len(adjust), ddim_steps=ddim_steps, scale=scale)
+                                  n_samples=len(adjust), ddim_steps=ddim_steps, scale=scale, x_T=x_T, step_noise=step_noise)
         for k, i in enumerate(adjust):
             stage1[i] = _to_uint8(imgs[k])
 
-    def stage2_call(i):
+    def stage2_call(anchors, x_T=None, step_noise=None):
         sampler = DDIMSampler(model)
-        imgs = sample_model_batch(model, sampler, _as_input(stage1[i], True).to(dev), DELTA_X_2, DELTA_Y_2, n_samples=4,
-                                  ddim_steps=stage2_steps, scale=scale)
-        for j in range(4):
-            stage2[f"{i}_{j}"] = _to_uint8(imgs[j])
+        ims = torch.cat([_as_input(stage1[i], True) for i in anchors]).to(dev)
+        imgs = sample_model_batch(model, sampler, ims, DELTA_X_2 * len(anchors), DELTA_Y_2 * len(anchors), n_samples=4,
+                                  ddim_steps=stage2_steps, scale=scale, x_T=x_T, step_noise=step_noise)
+        for a, i in enumerate(anchors):
+            for j in range(4):
+                stage2[f"{i}_{j}"] = _to_uint8(imgs[4 * a + j])
 
-    stage1_call(list(range(4)))
-    stage2_call(0)
-    pose = S.pose_json(float(polar_angle))
-    second = list(range(4, 8)) if polar_angle <= 75 else list(range(8, 12))
-    stage1_call(second)
-    for i in ([1, 2, 3] + second):
-        stage2_call(i)
+    if not batched:
+        stage1_call(first)
+        stage2_call([0])
+        stage1_call(second)
+        for i in ([1, 2, 3] + second):
+            stage2_call([i])
+    else:
+        n1 = ddim_iterations(ddim_steps, model.num_timesteps)
+        n2 = ddim_iterations(stage2_steps, model.num_timesteps)
+        draws = {}
+        for kind, key in [("s1", 0), ("s2", 0), ("s1", 1)] + [("s2", i) for i in [1, 2, 3] + second]:
+            # the reference's order of calls; inside a call: x_T, then one draw per iteration (ddim.py:137,223)
+            x_T = torch.randn(4, 4, 32, 32, device=dev)
+            draws[(kind, key)] = (x_T, [torch.randn(4, 4, 32, 32, device=dev) for _ in range(n1 if kind == "s1" else n2)])
+
+        def gather(keys, n):
+            return (torch.cat([draws[k][0] for k in keys]), [torch.cat([draws[k][1][i] for k in keys]) for i in range(n)])
+        stage1_call(first + second, *gather([("s1", 0), ("s1", 1)], n1))
+        anchors = first + second
+        stage2_call(anchors, *gather([("s2", i) for i in anchors], n2))
     if exp_dir is not None:
         from PIL import Image
         os.makedirs(os.path.join(exp_dir, "stage1_8"), exist_ok=True)

@@ -81,3 +81,43 @@ def test_ddim_sampler_matches_reference_trajectory(gold):
     assert np.array_equal(sampler.ddim_timesteps, gold["ddim_timesteps"])
     assert float((out.cpu() - torch.from_numpy(gold["ddim_out"])).abs().max()) < 2e-4
     assert "x_inter" in inter and "pred_x0" in inter
+
+
+def test_ddim_step_noise_is_the_global_generator_stream_drawn_early():
+    """Two sampler calls that draw from torch's CUDA generator as they go (the reference's behaviour), against ONE call over
+    the concatenated batch fed with the same draws made up front in the same order (zero123.generate_views, batched):
+    the same latents per view with a model that treats the images of a batch independently."""
+    from o2345.ddim import DDIMSampler
+    from oracle import ldm_oracle as LO
+    torch.backends.cudnn.allow_tf32 = False
+    toy = LO.ToyModel().to("cuda")
+    g = np.random.default_rng(9)
+    B = 2
+
+    def conds(n):
+        c = {"c_crossattn": [torch.from_numpy(g.standard_normal((n, 1, 768), dtype=np.float32)).cuda()],
+             "c_concat": [torch.from_numpy(g.standard_normal((n, 4, 32, 32), dtype=np.float32)).cuda()]}
+        u = {"c_crossattn": [torch.zeros(n, 1, 768, device="cuda")], "c_concat": [torch.zeros(n, 4, 32, 32, device="cuda")]}
+        return c, u
+    (c0, u0), (c1, u1) = conds(B), conds(B)
+    torch.cuda.manual_seed(77)
+    seq = []
+    for c, u in ((c0, u0), (c1, u1)):
+        out, _ = DDIMSampler(toy).sample(S=5, batch_size=B, shape=[4, 32, 32], conditioning=c, verbose=False, eta=1.0,
+                                         unconditional_guidance_scale=3.0, unconditional_conditioning=u)
+        seq.append(out)
+    torch.cuda.manual_seed(77)
+    draws = []
+    for _ in range(2):
+        x_T = torch.randn(B, 4, 32, 32, device="cuda")
+        draws.append((x_T, [torch.randn(B, 4, 32, 32, device="cuda") for _ in range(4)]))
+    cat = lambda a, b: {k: [torch.cat([a[k][0], b[k][0]])] for k in a}
+    out, _ = DDIMSampler(toy).sample(S=5, batch_size=2 * B, shape=[4, 32, 32], conditioning=cat(c0, c1), verbose=False, eta=1.0,
+                                     unconditional_guidance_scale=3.0, unconditional_conditioning=cat(u0, u1),
+                                     x_T=torch.cat([draws[0][0], draws[1][0]]),
+                                     step_noise=[torch.cat([draws[0][1][i], draws[1][1][i]]) for i in range(4)])
+    # the toy model is a cuDNN convolution, whose algorithm may change with the batch size: equal up to fp32 summation order
+    assert float((out[:B] - seq[0]).abs().max()) < 1e-5 and float((out[B:] - seq[1]).abs().max()) < 1e-5
+    with pytest.raises(ValueError):
+        DDIMSampler(toy).sample(S=5, batch_size=B, shape=[4, 32, 32], conditioning=c0, verbose=False, eta=1.0,
+                                unconditional_guidance_scale=3.0, unconditional_conditioning=u0, step_noise=draws[0][1][:3])

@@ -142,3 +142,9 @@ def test_command_lines_parse_the_reference_arguments():
                      "--resolution", "256"])
     with pytest.raises(SystemExit, match="only 'export_mesh' and 'val'"):
         runner.main(["--mode", "train"])
+
+
+def test_ddim_iteration_counts():
+    """76 / 49 UNet iterations for S = 75 / 50 (reference ddim.py:126-131 drops the schedule's last entry)."""
+    from o2345.zero123 import ddim_iterations
+    assert ddim_iterations(75) == 76 and ddim_iterations(50) == 49 and ddim_iterations(5) == 4
