@@ -306,6 +306,10 @@ int o2345_last_trap(char* buf, size_t n);
 /* Tuning hook (tools/gemm_sweep.py; not part of the data path): force the tile configuration of the following non-batched
  * GEMM / conv calls: ctas in {1, 2}, bn in {64, 128, 160, 256}, splits >= 1; 0 keeps the heuristic's choice of that field. */
 void o2345_debug_gemm_force(int ctas, int bn, int splits);
+/* Tuning hook: the persistent variant of the kernel (one CTA pair per SM pair walking many tiles, epilogue of tile i under
+ * the main loop of tile i + 1).  mode 0: heuristic (at least min_tiles pair tiles; min_tiles 0 = default), 1: wherever it is
+ * available (pair tiles of 128+ columns, staged fp16 epilogue, no split-K), 2: never. */
+void o2345_debug_gemm_persist(int mode, int min_tiles);
 /* Tuning hook: the seven constants of the tile-configuration cost model (per-SM ingest B/clk, two-CTA bonus, fabric B/clk,
  * fixed us, epilogue us per 160 columns, split-K us, split-K us per split and 128 columns); see gemm_tc.cu predict_us. */
 void o2345_debug_gemm_model(const float* seven);
@@ -339,6 +343,8 @@ int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G, float eps,
  * (no scratch, no global atomics).  Same result as o2345_groupnorm_stats + o2345_norm_act_im2col(ksize 1). */
 int o2345_groupnorm_apply(const void* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta, int act,
                           void* out, o2345_stream_t stream);
+/* Tuning hook (tools/gn_bench.py): CTAs per image (cluster size, a power of two <= 16) of o2345_groupnorm_apply; 0 = the launcher's rule. */
+void o2345_debug_groupnorm_cluster(int cl);
 /* out [B*Ho*Wo, k*k*C] (column order ky,kx,c) = patches of f(x), f = x * scale + shift (+SiLU if act) when scale != NULL.
  * upsample != 0: nearest x2 replication of x before the convolution.  Zero padding k/2 on the high side and
  * pad_lo on the low side (pad_lo < 0: k/2; pad_lo = 0 reproduces the VAE encoder's F.pad(x, (0,1,0,1))). */

@@ -51,7 +51,7 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;         // clears the CTA-rank bit o
 constexpr int MAX_CLUSTER = 16;                     // CTAS * splits: one cluster per tile (non-portable size, opted into per kernel)
 constexpr int RES_PREFETCH = 8;                     // 16-byte residual pieces per lane fetched before the accumulator is ready
 
-enum { WAIT_EMPTY = 1, WAIT_FULL = 2, WAIT_ACC = 3 };   // which wait timed out (o2345_last_trap)
+enum { WAIT_EMPTY = 1, WAIT_FULL = 2, WAIT_ACC = 3, WAIT_ACC_FREE = 4 };   // which wait timed out (o2345_last_trap)
 
 struct TrapRecord {
   unsigned long long magic;
@@ -459,7 +459,7 @@ __device__ __forceinline__ void splitk_finalize(const GemmParams& p, int m0, int
 }
 
 constexpr int EPI_RB_GROUPS = 8;                 // row-bias groups (images) one 128-row tile may span when staged in smem
-constexpr int epi_smem_bytes(int bn) { return bn * 4 + EPI_RB_GROUPS * bn * 2; }
+__host__ __device__ constexpr int epi_smem_bytes(int bn) { return bn * 4 + EPI_RB_GROUPS * bn * 2; }
 // the two column ranges of the eight epilogue warps split the tile at a multiple of 32 (a GEGLU chunk never straddles them)
 __host__ __device__ constexpr int col_split(int bn) { return ((bn / 2 + 31) / 32) * 32; }
 
@@ -588,7 +588,7 @@ __device__ __forceinline__ uint4 add_h8(uint4 v, uint4 q) {
 template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const WarpOut& g, uint32_t tmem_row_base, uint8_t* slab, int lane,
                                                 int m0, int row0, int n0, int c_lo, int c_hi, const float* sbias, const __half* srb,
-                                                const uint4 (&resq)[RES_PREFETCH]) {
+                                                const uint4 (&resq)[RES_PREFETCH], uint32_t release_bar = 0) {
   const int row = row0 + lane;
   // row-group bias of this thread's row: from the smem copy when the tile spans few groups, else straight from global
   const __half* rb = nullptr;
@@ -610,6 +610,11 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const WarpO
       case 2: stage_rows<2>(p, tmem_row_base, mine, n0, c_lo, c_hi, sbias, rb, rb_smem); break;
       default: stage_rows<4>(p, tmem_row_base, mine, n0, c_lo, c_hi, sbias, rb, rb_smem); break;
     }
+  }
+  if (release_bar) {   // persistent kernel: this warp has read its part of the accumulator buffer -- hand it back to the MMA issuer
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(release_bar) : "memory");
   }
   __syncwarp();
   __half* C = reinterpret_cast<__half*>(p.C);
@@ -698,6 +703,41 @@ constexpr int smem_bytes(int bn, int stages, int ctas) {
   return stages * (BM * BK * 2 + (bn / ctas) * BK * 2) + (2 * stages + 1) * 8 + 8 + 16 + epi_smem_bytes(bn) + 1024;
 }
 
+// One stage of the TMA producer: this CTA's 128 rows of A and its BROWS rows of the B tile for k-block kb of the tile at
+// (m0, n0).  Pair (CTAS = 2): the bytes of both CTAs are counted on the leader's full barrier.
+template <int CTAS, int BROWS>
+__device__ __forceinline__ void produce_stage(const GemmParams& p, const CUtensorMap* tmA, const CUtensorMap* tmB, uint8_t* a_dst,
+                                              uint8_t* b_dst, uint64_t* full_bar, int kb, int m0, int n0, uint32_t rank, int bz) {
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BROWS * BK * 2;
+  if (CTAS == 2) {
+    if (rank == 0) mbar_expect_tx(full_bar, 2 * (A_BYTES + B_BYTES));   // the peer's bytes land on this barrier too
+    const int nb = n0 + (int)rank * BROWS;
+    if (p.conv) {
+      const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
+      const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
+      tma2_load_4d(a_dst, tmA, full_bar, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+      tma2_load_2d(b_dst, tmB, full_bar, tap * p.cC + c0, nb);
+    } else {
+      tma2_load_2d(a_dst, tmA, full_bar, kb * BK, m0);
+      tma2_load_2d(b_dst, tmB, full_bar, kb * BK, nb);
+    }
+  } else {
+    mbar_expect_tx(full_bar, A_BYTES + B_BYTES);
+    if (p.conv) {
+      const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
+      const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
+      tma_load_4d(a_dst, tmA, full_bar, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+      tma_load_2d(b_dst, tmB, full_bar, tap * p.cC + c0, n0);
+    } else if (p.batched) {
+      tma_load_4d(a_dst, tmA, full_bar, kb * BK, m0, bz % p.nh, bz / p.nh);
+      tma_load_4d(b_dst, tmB, full_bar, kb * BK, n0, bz % p.nh, bz / p.nh);
+    } else {
+      tma_load_2d(a_dst, tmA, full_bar, kb * BK, m0);
+      tma_load_2d(b_dst, tmB, full_bar, kb * BK, n0);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 // Two CTAs per SM: their prologues / epilogues overlap each other's main loops.  (Measured alternative, dropped: one CTA per
 // SM with a ring twice as deep -- no gain on launches of <= 148 CTAs, 35 % slower on multi-wave launches: the main loops are
@@ -773,35 +813,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = (kb - kb0) % STAGES;
         const uint32_t ph = ((kb - kb0) / STAGES) & 1;
         mbar_wait(empty + s, ph ^ 1, p, WAIT_EMPTY, s);
-        uint8_t* a_dst = sA + s * A_BYTES;
-        uint8_t* b_dst = sB + s * B_BYTES;
-        if (CTAS == 2) {
-          if (rank == 0) mbar_expect_tx(full + s, 2 * (A_BYTES + B_BYTES));   // the peer's bytes land on this barrier too
-          const int nb = n0 + (int)rank * BROWS;
-          if (p.conv) {
-            const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
-            const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
-            tma2_load_4d(a_dst, &tmA, full + s, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
-            tma2_load_2d(b_dst, &tmB, full + s, tap * p.cC + c0, nb);
-          } else {
-            tma2_load_2d(a_dst, &tmA, full + s, kb * BK, m0);
-            tma2_load_2d(b_dst, &tmB, full + s, kb * BK, nb);
-          }
-        } else {
-          mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-          if (p.conv) {
-            const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
-            const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
-            tma_load_4d(a_dst, &tmA, full + s, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
-            tma_load_2d(b_dst, &tmB, full + s, tap * p.cC + c0, n0);
-          } else if (p.batched) {
-            tma_load_4d(a_dst, &tmA, full + s, kb * BK, m0, bz % p.nh, bz / p.nh);
-            tma_load_4d(b_dst, &tmB, full + s, kb * BK, n0, bz % p.nh, bz / p.nh);
-          } else {
-            tma_load_2d(a_dst, &tmA, full + s, kb * BK, m0);
-            tma_load_2d(b_dst, &tmB, full + s, kb * BK, n0);
-          }
-        }
+        produce_stage<CTAS, BROWS>(p, &tmA, &tmB, sA + s * A_BYTES, sB + s * B_BYTES, full + s, kb, m0, n0, rank, bz);
         if (kb == kb0) stamp(p, 2);
       }
       stamp(p, 3);
@@ -888,6 +900,142 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) stamp(p, 8);
 }
 
+
+// ------------------------------------------------------------------------------------------------ the persistent kernel
+// Problems with MANY tiles (the batched sampler calls: M = 16 384 ... 65 536 rows): one CTA pair per SM pair walks tiles
+// pair, pair + n_pairs, ... with TWO accumulator buffers in TMEM, so that
+//   * the epilogue of tile i (TMEM -> registers -> bias / activation / GEGLU -> shared-memory transpose -> global) runs
+//     under the main loop of tile i + 1 -- on short-K problems (K = 320: five k-blocks) the epilogue is as long as the main
+//     loop, and a CTA per tile serialises them (two resident CTAs per SM hide only part of it: 190 us against cuBLAS's 103
+//     on the 65536 x 2560 x 320 GEGLU projection);
+//   * the producer runs ahead across tile borders (the ring never drains), and barrier set-up, TMEM allocation, tensor-map
+//     fetch and tear-down are paid once per SM instead of once per tile.
+// Accumulator hand-over: acc_full[b] (tcgen05.commit, multicast to the pair) MMA -> epilogue warps of both CTAs;
+// acc_free[b] on the LEADER, 16 arrivals (eight epilogue warps x two CTAs, remote arrive from the peer) epilogue -> MMA.
+// The output transpose has its own shared memory (the ring is never idle), bias / row-bias slices are double-buffered.
+// Pair tiles only (CTAS = 2), staged fp16 epilogues only (MODE 0 / 1 / 2): everything else takes gemm_tc_kernel.
+constexpr int persist_smem_bytes(int bn, int stages) {
+  return stages * (BM * BK * 2 + (bn / 2) * BK * 2) + epi_slab_bytes(bn) + (2 * stages + 4) * 8 + 16 + 2 * epi_smem_bytes(bn) + 1024;
+}
+
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int BROWS = BN / 2;
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BROWS * BK * 2;
+  static_assert(B_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
+  static_assert(MODE != 3, "staged epilogues only");
+  constexpr int TCOLS = tmem_cols(BN);                       // one accumulator buffer; two are allocated
+  static_assert(2 * TCOLS <= 512, "two accumulator buffers must fit the 512 TMEM columns");
+  constexpr int CSPLIT = col_split(BN);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* slabs = sB + STAGES * B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(slabs + epi_slab_bytes(BN));
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_free = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+  float* sbias0 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~(uintptr_t)15);
+  constexpr int EPI_FLOATS = epi_smem_bytes(BN) / 4;         // one bias + row-bias buffer, in floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;
+  const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1u));
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int ntiles = ((p.M + 2 * BM - 1) / (2 * BM)) * tiles_n;
+  const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+    for (int b = 0; b < 2; ++b) mbar_init(acc_full + b, 1), mbar_init(acc_free + b, 2 * EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * TCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer: runs ahead across tile borders, bounded only by the ring
+      uint32_t cnt = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        const int tm = t / tiles_n, n0 = (t - tm * tiles_n) * BN, m0 = tm * (2 * BM) + (int)rank * BM;
+        for (int kb = 0; kb < nk; ++kb, ++cnt) {
+          const int s = cnt % STAGES;
+          mbar_wait(empty + s, ((cnt / STAGES) & 1) ^ 1, p, WAIT_EMPTY, s);
+          produce_stage<2, BROWS>(p, &tmA, &tmB, sA + s * A_BYTES, sB + s * B_BYTES, full + s, kb, m0, n0, rank, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ---------------- MMA issuer (leader CTA): tile i into accumulator buffer i & 1
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+      uint32_t cnt = 0, it = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(acc_free + buf, ((it >> 1) & 1) ^ 1, p, WAIT_ACC_FREE, (int)buf);   // both CTAs' epilogue warps have drained tile it - 2
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + buf * TCOLS;
+        for (int kb = 0; kb < nk; ++kb, ++cnt) {
+          const int s = cnt % STAGES;
+          mbar_wait(full + s, (cnt / STAGES) & 1, p, WAIT_FULL, s);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16<2>(acc, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0);
+          umma_commit<2>(empty + s, pair_mask);
+        }
+        umma_commit<2>(acc_full + buf, pair_mask);
+      }
+    }
+  } else {  // ------------------------ epilogue warps 2..9: this CTA's 128 accumulator rows of every tile
+    const int e = warp - 2, quarter = warp & 3, te = threadIdx.x - 64;
+    const int c_lo = e < 4 ? 0 : CSPLIT, c_hi = e < 4 ? CSPLIT : BN;
+    uint8_t* slab = slabs + e * 32 * (CSPLIT * 2 + 16);
+    // the leader's acc_free barriers, as shared::cluster addresses (the peer arrives remotely)
+    uint32_t free_bar0;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(free_bar0) : "r"(smem_u32(acc_free)), "r"(crank & ~1u));
+    uint32_t it = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++it) {
+      const uint32_t buf = it & 1;
+      const int tm = t / tiles_n, n0 = (t - tm * tiles_n) * BN, m0 = tm * (2 * BM) + (int)rank * BM;
+      const int row0 = m0 + quarter * 32;
+      float* sbias = sbias0 + buf * EPI_FLOATS;
+      __half* srb = reinterpret_cast<__half*>(sbias + BN);
+      epilogue_preload<BN>(p, m0, n0, sbias, srb, te);
+      const WarpOut g = warp_out<MODE>(p, n0, c_lo, c_hi);
+      uint4 resq[RES_PREFETCH];
+      prefetch_residual(p, g, lane, row0, resq);
+      mbar_wait(acc_full + buf, (it >> 1) & 1, p, WAIT_ACC, (int)buf);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_row_base = tmem_base + buf * TCOLS + ((uint32_t)(quarter * 32) << 16);
+      epilogue_staged<BN, MODE>(p, g, tmem_row_base, slab, lane, m0, row0, n0, c_lo, c_hi, sbias, srb, resq, free_bar0 + buf * 8);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or the peer's TMEM reads are in flight
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TCOLS));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -945,11 +1093,14 @@ TrapRecord* diag_buffer(cudaStream_t st) {
 
 struct Config {
   int ctas, bn, splits;
+  int persist;   // 1: gemm_tc_persistent_kernel (pair tiles, staged epilogue, many tiles)
 };
 
 // tuning / sweep hook: O2345_GEMM_FORCE="ctas,bn,splits" (0 = keep the heuristic's choice for that field); also settable
 // through o2345_debug_gemm_force (tools/gemm_sweep.py)
 int g_force[3] = {-1, 0, 0};
+int g_persist = 0;          // 0: heuristic, 1: persistent kernel wherever it is available, 2: never (o2345_debug_gemm_persist)
+int g_persist_min_tiles = 0;   // heuristic threshold override (0: default)
 void read_force_env() {
   if (g_force[0] >= 0) return;
   g_force[0] = g_force[1] = g_force[2] = 0;
@@ -993,6 +1144,7 @@ Config pick_config(const GemmParams& p, int nk, bool can_split, int64_t ws_float
   read_force_env();
   Config c;
   const int M = p.M, N = p.N;
+  c.persist = 0;
   if (p.batched) {
     c.ctas = 1, c.bn = N <= 64 ? 64 : 128, c.splits = 1;
     return c;
@@ -1025,6 +1177,17 @@ Config pick_config(const GemmParams& p, int nk, bool can_split, int64_t ws_float
     c.bn = (g_force[1] == 64 || g_force[1] == 128 || (c.ctas == 2 && (g_force[1] == 160 || g_force[1] == 256))) ? g_force[1] : 128;
     c.splits = 1;
   }
+  // Many tiles and a short K (the batched sampler calls: M = 16 384 ... 65 536): the epilogue of a tile is as long as its main
+  // loop, and the persistent kernel hides it under the next tile's.  Measured per shape (tools/gemm_persist_ab.py, B200):
+  // 65536 x 2560 x 320 GEGLU 184 -> 157 us, 65536 x 960 x 320 75 -> 59, 65536 x 320 x 1280 85 -> 63, 16384 x 1920 x 640 51 -> 38;
+  // with long K it LOSES (65536 x 320 x 2880 conv 111 -> 141 us): one CTA per SM keeps 128-156 KB of operands in flight
+  // against 192-208 KB for two resident per-tile CTAs, and the main loop is bound by bytes in flight.
+  if (g_persist == 0 && g_force[0] == 0 && g_force[1] == 0 && g_force[2] == 0 && !p.out_f32 && nk <= 20) {
+    const int bn_p = N >= 512 ? 256 : 160;
+    const int tiles = cdiv(M, 2 * BM) * cdiv(N, bn_p);
+    const int min_tiles = g_persist_min_tiles > 0 ? g_persist_min_tiles : sm_count() / 2;
+    if (tiles >= min_tiles && (N >= 512 || nk >= 8)) c.ctas = 2, c.bn = bn_p, c.splits = 1, c.persist = 1;
+  }
   return c;
 }
 
@@ -1035,6 +1198,13 @@ int pick_mode(const GemmParams& p, const Config& c) {
                       (!p.residual || ((uintptr_t)p.residual % 16) == 0) && !(c.ctas == 1 && p.act == 3);
   if (!staged) return 3;
   return p.act == 0 ? 0 : (p.act == 3 ? 1 : 2);
+}
+
+// The persistent kernel (mode 0 / 1 / 2 epilogues, pair tiles): chosen by pick_config for many-tile short-K problems, or forced
+// by the tuning hook wherever it is available.
+bool pick_persist(const Config& c, int mode) {
+  if (g_persist == 2 || mode == 3 || c.ctas != 2 || c.splits > 1 || c.bn < 128) return false;
+  return g_persist == 1 || c.persist == 1;
 }
 
 long long* g_trace = nullptr;
@@ -1060,6 +1230,32 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, GemmParams p, int batch, 
   return O2345_OK;
 }
 
+template <int BN, int STAGES, int MODE>
+int launch_persistent(const CUtensorMap& a, const CUtensorMap& b, GemmParams p, cudaStream_t st) {
+  constexpr int SMEM = persist_smem_bytes(BN, STAGES);
+  static_assert(SMEM <= 227 * 1024, "one CTA per SM");
+  static PerDeviceOnce attr;
+  if (attr.need())
+    O2345_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  p.bn = BN, p.ctas = 2, p.mode = MODE + 10;
+  p.diag = diag_buffer(st);
+  p.splits = 1;
+  const int tiles = cdiv(p.M, 2 * BM) * cdiv(p.N, BN), pairs = sm_count() / 2;
+  dim3 grid(2 * (tiles < pairs ? tiles : pairs), 1, 1);
+  O2345_CUDA(launch_pdl_cluster(gemm_tc_persistent_kernel<BN, STAGES, MODE>, grid, dim3(GEMM_THREADS), (size_t)SMEM, st, 2, 1, a, b, p));
+  O2345_LAUNCH_CHECK();
+  return O2345_OK;
+}
+
+template <int BN, int STAGES>
+int launch_persistent_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+  switch (mode) {
+    case 0: return launch_persistent<BN, STAGES, 0>(a, b, p, st);
+    case 1: return launch_persistent<BN, STAGES, 1>(a, b, p, st);
+    default: return launch_persistent<BN, STAGES, 2>(a, b, p, st);
+  }
+}
+
 template <int BN, int STAGES, int CTAS>
 int launch_mode(int mode, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int batch, cudaStream_t st) {
   switch (mode) {
@@ -1076,6 +1272,11 @@ int dispatch(const Config& c, int mode, const CUtensorMap& a, const CUtensorMap&
   if (p.colstats && mode == 3 && c.splits <= 1) {
     set_error("o2345_gemm_f16: column statistics need the staged fp16 epilogue (16-byte aligned C / residual) or split-K");
     return O2345_EUNSUPPORTED;
+  }
+  if (pick_persist(c, mode)) {
+    if (c.bn == 128) return launch_persistent_mode<128, 6>(mode, a, b, p, st);
+    if (c.bn == 160) return launch_persistent_mode<160, 6>(mode, a, b, p, st);
+    return launch_persistent_mode<256, 4>(mode, a, b, p, st);
   }
   if (c.ctas == 2) {
     if (c.bn == 64) return launch_mode<64, 5, 2>(mode, a, b, p, batch, st);
@@ -1126,6 +1327,8 @@ extern "C" void o2345_debug_gemm_force(int ctas, int bn, int splits) {
 }
 
 
+extern "C" void o2345_debug_gemm_persist(int mode, int min_tiles) { g_persist = mode, g_persist_min_tiles = min_tiles; }
+
 extern "C" void o2345_debug_gemm_model(const float* seven) {
   for (int i = 0; i < 7; ++i) g_model[i] = seven[i];
 }
@@ -1136,12 +1339,13 @@ extern "C" int o2345_last_trap(char* buf, size_t n) {
   const TrapRecord* d = g_diag;
   if (!d || d->magic != TRAP_MAGIC) return 0;
   static const char* names[] = {"?", "empty (producer waiting for the MMA to free a stage)", "full (MMA issuer waiting for TMA bytes)",
-                                "accumulator (epilogue waiting for the last MMA)"};
+                                "accumulator (epilogue waiting for the last MMA)",
+                                "accumulator buffer (MMA issuer waiting for the epilogue warps to drain it)"};
   snprintf(buf, n,
            "gemm_tc_kernel<BN=%d, CTAS=%d, MODE=%d> M=%d N=%d K=%d conv=%d splits=%d: CTA (%d,%d,%d) rank %d gave up after 4 s "
            "on barrier '%s' stage %d",
            d->bn, d->ctas, d->mode, d->M, d->N, d->K, d->conv, d->splits, d->bx, d->by, d->bz, d->rank,
-           names[d->tag >= 1 && d->tag <= 3 ? d->tag : 0], d->stage);
+           names[d->tag >= 1 && d->tag <= 4 ? d->tag : 0], d->stage);
   return 1;
 }
 

@@ -204,22 +204,29 @@ __global__ void norm_act_im2col_stats_kernel(const __half* __restrict__ x, int H
 }
 
 // GroupNorm (+SiLU) of a whole activation in ONE kernel (ksize 1: the implicit-conv and transformer inputs, 55 of the 61 GroupNorms
-// of a UNet pass): an image is handled by one thread-block CLUSTER of CL CTAs.  Pass 1: every CTA sums its slab of pixels
-// (16-byte loads, a thread keeps its 8-channel slot) into per-group shared-memory sums; the CL partial sums are exchanged
-// through distributed shared memory (ld.shared::cluster) around one cluster barrier; pass 2: the slab is read again (L2
-// resident), normalised and written.  Replaces groupnorm_stats (global atomics + ticket + last-CTA finalize) followed by
-// norm_act_im2col: one launch instead of two, no global atomics, no scratch.
+// of a UNet pass): an image is handled by one thread-block CLUSTER of CL CTAs.  Pass 1: every CTA reads its slab of pixels
+// ONCE (16-byte loads, four in flight per thread, a thread keeps its 8-channel slot), parks it in shared memory (KEEP) and sums
+// it into per-group shared-memory sums; the CL partial sums are exchanged through distributed shared memory
+// (ld.shared::cluster) around one cluster barrier; pass 2 normalises the parked slab and writes it: x is read once and y
+// written once -- the traffic floor of the operation.  (Slabs over 200 KB per CTA -- not reached by the UNet / VAE shapes at
+// the cluster sizes the launcher picks -- re-read x from L2 instead.)  Replaces groupnorm_stats (global atomics + ticket +
+// last-CTA finalize) followed by norm_act_im2col: one launch instead of two, no global atomics, no scratch.
+// Round-2 history: the first version read one 16-byte piece per thread and iteration in both passes and summed the 16 remote
+// partials with dependent loads: 21-28 us per launch at the batched sampler sizes, a sixth of what the traffic needs.
+template <bool KEEP>
 __global__ void groupnorm_apply_cluster_kernel(const __half* __restrict__ x, int HW, int C, int G, float eps,
                                                const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                                __half* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float gsm[];           // [2 G] this CTA's sums, then [2 G] mean / rstd
+  extern __shared__ __align__(16) float gsm[];           // [2 G] this CTA's sums, [2 G] the image's sums, then (KEEP) the slab
+  constexpr int U = 4;
   uint32_t rank, csize;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
   const int b = blockIdx.y, cg = C / G, c8n = C >> 3;
   const int slot = threadIdx.x % c8n, prow = threadIdx.x / c8n, rows = blockDim.x / c8n;   // blockDim is a multiple of c8n
+  uint4* slab = reinterpret_cast<uint4*>(gsm + ((4 * G + 3) & ~3));
   for (int i = threadIdx.x; i < 4 * G; i += blockDim.x) gsm[i] = 0.f;
   __syncthreads();
   const int P = (HW + (int)csize - 1) / (int)csize;
@@ -228,14 +235,21 @@ __global__ void groupnorm_apply_cluster_kernel(const __half* __restrict__ x, int
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = 0.f, q[e] = 0.f;
-  for (int pix = p0 + prow; pix < p1; pix += rows) {
-    const uint4 v = *reinterpret_cast<const uint4*>(base + (int64_t)pix * C);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
+  for (int pix = p0 + prow; pix < p1; pix += U * rows) {
+    uint4 v[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(h[e]);
-      s[2 * e] += f.x, q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
-      s[2 * e + 1] += f.y, q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
+    for (int u = 0; u < U; ++u)
+      v[u] = pix + u * rows < p1 ? *reinterpret_cast<const uint4*>(base + (int64_t)(pix + u * rows) * C) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (KEEP && pix + u * rows < p1) slab[(pix + u * rows - p0) * c8n + slot] = v[u];
+      const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        s[2 * e] += f.x, q[2 * e] = fmaf(f.x, f.x, q[2 * e]);
+        s[2 * e + 1] += f.y, q[2 * e + 1] = fmaf(f.y, f.y, q[2 * e + 1]);
+      }
     }
   }
   {
@@ -252,15 +266,20 @@ __global__ void groupnorm_apply_cluster_kernel(const __half* __restrict__ x, int
   // every CTA's partial sums become visible to the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
-    float t = 0.f;
     const uint32_t local = (uint32_t)__cvta_generic_to_shared(gsm + i);
-    for (uint32_t r = 0; r < csize; ++r) {
-      uint32_t remote;
-      float v;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-      t += v;
+    float part[16];                                        // the (up to 16) remote loads are independent: one round trip
+#pragma unroll
+    for (uint32_t r = 0; r < 16; ++r) {
+      part[r] = 0.f;
+      if (r < csize) {
+        uint32_t remote;
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(part[r]) : "r"(remote));
+      }
     }
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += part[r];
     gsm[2 * G + i] = t;
   }
   __syncthreads();
@@ -276,18 +295,28 @@ __global__ void groupnorm_apply_cluster_kernel(const __half* __restrict__ x, int
     sv[e] = r * ga, tv[e] = be - m * r * ga;
   }
   __half* obase = out + (int64_t)b * HW * C + slot * 8;
-  for (int pix = p0 + prow; pix < p1; pix += rows) {
-    const uint4 v = *reinterpret_cast<const uint4*>(base + (int64_t)pix * C);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-    __half2 r[4];
+  for (int pix = p0 + prow; pix < p1; pix += U * rows) {
+    uint4 v[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(h[e]);
-      f.x = fmaf(f.x, sv[2 * e], tv[2 * e]), f.y = fmaf(f.y, sv[2 * e + 1], tv[2 * e + 1]);
-      if (act) f.x = silu(f.x), f.y = silu(f.y);
-      r[e] = __floats2half2_rn(f.x, f.y);
+    for (int u = 0; u < U; ++u) {
+      const int pu = pix + u * rows;
+      if (pu < p1) v[u] = KEEP ? slab[(pu - p0) * c8n + slot] : *reinterpret_cast<const uint4*>(base + (int64_t)pu * C);
     }
-    *reinterpret_cast<uint4*>(obase + (int64_t)pix * C) = *reinterpret_cast<uint4*>(r);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pu = pix + u * rows;
+      if (pu >= p1) break;
+      const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+      __half2 r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h[e]);
+        f.x = fmaf(f.x, sv[2 * e], tv[2 * e]), f.y = fmaf(f.y, sv[2 * e + 1], tv[2 * e + 1]);
+        if (act) f.x = silu(f.x), f.y = silu(f.y);
+        r[e] = __floats2half2_rn(f.x, f.y);
+      }
+      *reinterpret_cast<uint4*>(obase + (int64_t)pu * C) = *reinterpret_cast<uint4*>(r);
+    }
   }
 }
 
@@ -534,6 +563,9 @@ extern "C" int o2345_groupnorm_stats(const void* x, int B, int HW, int C, int G,
   return O2345_OK;
 }
 
+static int g_gn_cluster = 0;   // tuning hook: CTAs per image of the one-kernel GroupNorm (0: the launcher's rule)
+extern "C" void o2345_debug_groupnorm_cluster(int cl) { g_gn_cluster = cl; }
+
 extern "C" int o2345_groupnorm_apply(const void* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta,
                                      int act, void* out, o2345_stream_t stream) {
   O2345_CHECK_ARG(x && out && B > 0 && HW > 0 && G > 0 && G <= 256 && C % G == 0, "bad arguments");
@@ -542,22 +574,40 @@ extern "C" int o2345_groupnorm_apply(const void* x, int B, int HW, int C, int G,
   const int c8n = C / 8;
   const int rows = c8n >= 512 ? 1 : 512 / c8n;
   const int threads = c8n * rows;
-  // CTAs per image = cluster size: enough to spread an image over 1 / B of the GPU, at most 16 (non-portable size), and no
-  // more than the image has pixel rows for
-  int cl = 16;
-  while (cl > 1 && (cl * B > 2 * sm_count() || HW < cl * rows)) cl >>= 1;
+  // CTAs per image = cluster size (a power of two <= 16, a non-portable size).  Measured on a B200 (tools/gn_bench.py,
+  // profiles/r2_gn_cluster_sweep.txt): the kernel is fastest when the whole launch is about ONE CTA per SM -- clusters of 16
+  // over a batch of 64 images (1 024 small CTAs, few 16-wide clusters schedulable at a time) took 2-3x longer than clusters
+  // of 2 -- except that slabs beyond ~400 KB per CTA want one more doubling.  Never more CTAs than the image has pixel rows.
+  int cl = 1;
+  while (cl < 16 && (int64_t)2 * cl * B <= (int64_t)sm_count()) cl <<= 1;
+  if (cl < 16 && (int64_t)HW * C * 2 / cl > 400 * 1024) cl <<= 1;
+  while (cl > 1 && HW < cl * rows) cl >>= 1;
+  if (g_gn_cluster > 0) {
+    cl = g_gn_cluster;
+    while (cl > 1 && HW < cl * rows) cl >>= 1;
+  }
+  const size_t sums = (size_t)((4 * G + 3) & ~3) * sizeof(float);
+  const size_t slab = (size_t)cdiv(HW, cl) * C * 2;
+  const bool keep = sums + slab <= 200 * 1024;
   static PerDeviceOnce attr;
-  if (attr.need()) O2345_CUDA(cudaFuncSetAttribute(groupnorm_apply_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (attr.need()) {
+    O2345_CUDA(cudaFuncSetAttribute(groupnorm_apply_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    O2345_CUDA(cudaFuncSetAttribute(groupnorm_apply_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    O2345_CUDA(cudaFuncSetAttribute(groupnorm_apply_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(cl, B), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = 4 * G * sizeof(float), cfg.stream = ST;
+  cfg.gridDim = dim3(cl, B), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = sums + (keep ? slab : 0), cfg.stream = ST;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   at[1].id = cudaLaunchAttributeClusterDimension;
   at[1].val.clusterDim.x = cl, at[1].val.clusterDim.y = 1, at[1].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = 2;
-  O2345_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_apply_cluster_kernel, (const __half*)x, HW, C, G, eps, gamma, beta, act, (__half*)out));
+  if (keep)
+    O2345_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_apply_cluster_kernel<true>, (const __half*)x, HW, C, G, eps, gamma, beta, act, (__half*)out));
+  else
+    O2345_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_apply_cluster_kernel<false>, (const __half*)x, HW, C, G, eps, gamma, beta, act, (__half*)out));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -83,6 +83,8 @@ _SIGS = {
                                  c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
     "o2345_debug_gemm_trace": (None, [c_fp]),
     "o2345_debug_gemm_force": (None, [C.c_int, C.c_int, C.c_int]),
+    "o2345_debug_gemm_persist": (None, [C.c_int, C.c_int]),
+    "o2345_debug_groupnorm_cluster": (None, [C.c_int]),
     "o2345_debug_gemm_model": (None, [C.POINTER(C.c_float)]),
     "o2345_last_trap": (C.c_int, [C.c_char_p, C.c_size_t]),
     "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64,

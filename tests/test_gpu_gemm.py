@@ -203,3 +203,63 @@ def test_epilogue_groupnorm_statistics_feed_the_next_norm(B, H, W, C, N, split):
     sc, sh = ops_a.groupnorm_stats(y, B, HW, N, 32, 1e-5, gamma[:N], beta[:N])
     want3, _, _ = ops_a.norm_act_im2col(y, B, H, W, N, 3, 2, False, (sc, sh), True)
     assert (Ho, Wo) == (H // 2, W // 2) and float((got3.float() - want3.float()).abs().max()) < 2e-2
+
+
+@pytest.fixture
+def persistent_everywhere():
+    """Forces the persistent variant of the GEMM kernel wherever it is available (pair tiles >= 128 columns, staged fp16
+    epilogue), whatever the tile count; restores the heuristic afterwards."""
+    from o2345 import _lib
+    lib = _lib.load()
+    lib.o2345_debug_gemm_persist(1, 0)
+    yield lib
+    lib.o2345_debug_gemm_persist(0, 0)
+    lib.o2345_debug_gemm_force(0, 0, 0)
+
+
+@pytest.mark.parametrize("bn", [128, 160, 256])
+@pytest.mark.parametrize("M,N,K", [(65536, 320, 320), (16384, 640, 640), (40000, 960, 328), (300, 192, 72), (8192, 2560, 64),
+                                   (33000, 1280, 1280)])
+def test_persistent_kernel_matches_matmul(persistent_everywhere, bn, M, N, K):
+    """One CTA pair per SM pair walking many tiles with two TMEM accumulator buffers: every tile width, one to ~40 tiles per
+    pair, M tails inside a pair and inside the first CTA, N tails, K tails, a single k-block (the accumulator hand-over is
+    then the only thing between two tiles), bias + residual + activation and GEGLU epilogues."""
+    from o2345 import ops_a
+    persistent_everywhere.o2345_debug_gemm_force(2, bn, 1)
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + bn)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) * 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).half()
+    tol = 4e-3 * (K ** 0.5) + 2e-2                                  # fp16 output rounding + summation order
+    out = ops_a.gemm(a, b)
+    assert out.dtype == torch.float16
+    assert (out.float() - ref(a, b)).abs().max().item() <= tol
+    for act in (0, 1):
+        out = ops_a.gemm(a, b, bias=bias, residual=res, act=act)
+        assert (out.float() - ref(a, b, bias, res, act)).abs().max().item() <= tol
+    if N % 64 == 0:
+        wp, bp = ops_a.geglu_pack(b, bias)
+        out = ops_a.gemm(a, wp, bias=bp, act=ops_a.ACT_GEGLU)
+        y = a.float() @ b.float().t() + bias
+        want = y[:, :N // 2] * torch.nn.functional.gelu(y[:, N // 2:])
+        assert ((out.float() - want).abs() - 2e-3 * want.abs()).max().item() <= tol          # fp16 output: relative on the large values
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(64, 32, 32, 320, 320), (16, 16, 16, 640, 640), (64, 8, 8, 1280, 1280), (3, 64, 64, 128, 128)])
+def test_persistent_kernel_implicit_conv(persistent_everywhere, B, H, W, C, N):
+    """The implicit 3x3 convolution (nine shifted TMA boxes per channel block) through the persistent kernel, with the
+    ResBlock epilogue: bias + per-image embedding row bias, then the skip connection."""
+    from o2345 import ops_a
+    g = torch.Generator(device="cuda").manual_seed(B + H + C)
+    x = (torch.randn(B, H, W, C, device="cuda", generator=g) * 0.5).half()
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) * (2.0 / (9 * C)) ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    emb = torch.randn(B, N, device="cuda", generator=g).half()
+    res = torch.randn(B * H * W, N, device="cuda", generator=g).half()
+    wk = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    conv = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    out = ops_a.conv3x3(x.view(-1, C), B, H, W, C, wk, bias=bias, rowbias=emb)
+    assert (out.float() - (conv + emb.float().repeat_interleave(H * W, 0))).abs().max().item() < 2e-2
+    out = ops_a.conv3x3(x.view(-1, C), B, H, W, C, wk, bias=bias, residual=res)
+    assert (out.float() - (conv + res.float())).abs().max().item() < 2e-2

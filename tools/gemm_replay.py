@@ -70,9 +70,29 @@ del g, ops
 DEF = [40, 0.5, 6300, 5, 3, 4, 1]
 def model(v): lib.o2345_debug_gemm_model((C.c_float * 7)(*v))
 print("%d launches" % len(rec))
-CASES = [("default", (0, 0, 0), DEF), ("no split", (0, 0, 1), DEF), ("bn160", (0, 160, 0), DEF), ("bn128", (0, 128, 0), DEF),
-         ("split cost x2", (0, 0, 0), [40, 0.5, 6300, 5, 3, 8, 2])]
-for label, force, mv in CASES:
-    lib.o2345_debug_gemm_force(*force); model(mv)
-    print("%-22s %.3f ms" % (label, replay_ms()), flush=True)
+CASES = [("default", (0, 0, 0), DEF, (0, 0)), ("never persistent", (0, 0, 0), DEF, (2, 0)), ("persistent everywhere", (0, 0, 0), DEF, (1, 0)),
+         ("persistent >= 74 tiles", (0, 0, 0), DEF, (0, 74)), ("persistent >= 296 tiles", (0, 0, 0), DEF, (0, 296)),
+         ("persistent >= 592 tiles", (0, 0, 0), DEF, (0, 592)), ("default again", (0, 0, 0), DEF, (0, 0))]
+# one graph per case (the kernel choice is frozen at capture), then the cases are timed in turn, round after round, so that
+# clock / power drift over the run hits all of them alike
+def capture():
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        for name, a, k in rec: real[name](*a, **k)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            for name, a, k in rec: real[name](*a, **k)
+    g.replay(); torch.cuda.synchronize()
+    return g
+graphs = []
+for label, force, mv, pers in CASES:
+    lib.o2345_debug_gemm_force(*force); model(mv); lib.o2345_debug_gemm_persist(*pers)
+    graphs.append((label, capture(), []))
+lib.o2345_debug_gemm_persist(0, 0)
 lib.o2345_debug_gemm_force(0, 0, 0); model(DEF)
+for rnd in range(6):
+    for label, g, ts in graphs:
+        for _ in range(3):
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+for label, g, ts in graphs:
+    print("%-30s %.3f ms (min %.3f)" % (label, float(np.median(ts)), min(ts)), flush=True)

@@ -1,30 +1,43 @@
-"""Device time of the captured UNet graph (CFG batch 8) under the knobs given in the environment:
-O2345_PDL=0, O2345_GEMM_FORCE=ctas,bn,splits, O2345_FUSE_GN=0.  Prints one line."""
+"""Device time of the captured UNet graph under a list of knob settings, all in ONE process on ONE GPU, the graphs of the
+cases replayed in turn round after round (box-to-box and over-the-run drift is larger than most of the effects):
+    python tools/unet_ab.py [batch ...]           (default 16 64)
+Knobs: the persistent GEMM variant (o2345_debug_gemm_persist), the GroupNorm cluster size (o2345_debug_groupnorm_cluster),
+the one-kernel GroupNorm (net.gn_one_kernel)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "one-2-3-45_b200")):
     sys.path.insert(0, p)
+import numpy as np
 import torch
 from o2345 import _lib
 from o2345.unet import UNetModel
+lib = _lib.load()
 net = UNetModel().cuda().requires_grad_(False)
-if "O2345_FUSE_GN" in os.environ:
-    net.fuse_gn_stats = os.environ["O2345_FUSE_GN"] != "0"
-if "O2345_GN_ONE" in os.environ:
-    net.gn_one_kernel = os.environ["O2345_GN_ONE"] != "0"
-x = torch.randn(8, 8, 32, 32, device="cuda"); t = torch.full((8,), 501, device="cuda"); ctx = torch.randn(8, 1, 768, device="cuda")
-for _ in range(3):
-    net(x, t, ctx)
-torch.cuda.synchronize()
-graph = net._graphs[next(iter(net._graphs))][0]
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-ts = []
-for _ in range(5):
-    a.record()
-    for _ in range(10):
-        graph.replay()
-    b.record(); torch.cuda.synchronize()
-    ts.append(a.elapsed_time(b) / 10)
-_lib.reset_launches(); net(x, t, ctx)
-print("UNet graph %.3f ms (min %.3f)  kernels %d  env %s" % (sorted(ts)[2], min(ts), _lib.launches(),
-      {k: v for k, v in os.environ.items() if k.startswith("O2345_")}))
+CASES = [("default", {}), ("GEMM never persistent", {"persist": (2, 0)}), ("GroupNorm clusters of 16", {"gn_cl": 16}),
+         ("GroupNorm two kernels", {"gn_one": False}), ("default again", {})]
+if os.environ.get("UNET_AB_CASES"):
+    CASES = eval(os.environ["UNET_AB_CASES"])
+for B in [int(a) for a in sys.argv[1:]] or [16, 64]:
+    x = torch.randn(B, 8, 32, 32, device="cuda"); t = torch.full((B,), 501, device="cuda"); ctx = torch.randn(B, 1, 768, device="cuda")
+    graphs = []
+    for label, knobs in CASES:
+        lib.o2345_debug_gemm_persist(*knobs.get("persist", (0, 0)))
+        lib.o2345_debug_groupnorm_cluster(knobs.get("gn_cl", 0))
+        lib.o2345_debug_gemm_force(*knobs.get("force", (0, 0, 0)))
+        net.gn_one_kernel = knobs.get("gn_one", True)
+        net._graphs.clear()
+        for _ in range(2):
+            net(x, t, ctx)
+        torch.cuda.synchronize()
+        graphs.append((label, net._graphs[next(iter(net._graphs))], []))
+    lib.o2345_debug_gemm_persist(0, 0); lib.o2345_debug_groupnorm_cluster(0); lib.o2345_debug_gemm_force(0, 0, 0); net.gn_one_kernel = True
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rnd in range(6):
+        for label, g, ts in graphs:
+            a.record()
+            for _ in range(5):
+                g[0].replay()
+            b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / 5)
+    for label, g, ts in graphs:
+        print("batch %3d  %-28s %.3f ms (min %.3f)  kernels %d" % (B, label, float(np.median(ts)), min(ts), g[5]), flush=True)
