@@ -20,6 +20,7 @@
 // Numerics: features, statistics, softmax and the colour blend are fp32; only MMA operands are rounded to fp16
 // (|rel| 5e-4), which moves the blended colours by ~1e-3.  The fp32 kernel stays available (precision = 0) and is the
 // one the tight oracle parity tests use.
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -29,7 +30,8 @@ namespace o2345 {
 namespace {
 using namespace rpack;
 
-constexpr int TW = 10;  // warps per CTA (2 CTAs per SM: 20 warps; r1: 16 warps were latency / instruction-fetch bound)
+// warps per CTA = template parameter TW of the kernel: 10 (two CTAs per SM) or 20 (ONE CTA per SM: all 20 warps of the SM start
+// every sample together, see `lockstep`, and the 48 KB of fp16 weights are staged once per SM)
 
 // fp16 weights in shared memory: matrix [n][LD], LD = K + 8 halves (conflict-free 32-bit loads by (g, t))
 constexpr int LD16 = 24, LD32 = 40, LD48 = 56, LD64 = 72, LD144 = 152;
@@ -50,7 +52,7 @@ constexpr int F_D0B = 0, F_D1B = 16, F_B0B = 80, F_B1B = 144, F_V0B = 176, F_V1B
               F_R1B = 304, F_R2W = 312, F_R2B = 320, F_S = 321, F_TOTAL = 324;
 constexpr int REC = 12;                     // floats per view record
 constexpr int WARP_SMEM = 32 * REC * 4 + 2 * 16 * 32 * 4;
-constexpr int TC_SMEM = H_TOTAL * 2 + F_TOTAL * 4 + TW * WARP_SMEM;
+constexpr int tc_smem(int tw) { return H_TOTAL * 2 + F_TOTAL * 4 + tw * WARP_SMEM; }
 static_assert((H_TOTAL * 2) % 16 == 0, "bias block must stay 16-byte aligned");
 
 // Branch-free ELU: one MUFU.EX2 on min(x, 0) and a select (the ternary around __expf compiled to a divergent branch per
@@ -174,11 +176,12 @@ __device__ void fill_w(__half* dst, int LD, int n_rows, int col0, int k_span, co
   }
 }
 
-__global__ void __launch_bounds__(TW * 32, 2)
+template <int TW>
+__global__ void __launch_bounds__(TW * 32, 20 / TW)
 render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ active, const float* __restrict__ vol,
                        const float* __restrict__ occ, int D, o2345_views views, int dir_mode,
                        const float* __restrict__ query_center, const float* __restrict__ dirs,
-                       const float* __restrict__ pack, float* __restrict__ rgb_out, int32_t* __restrict__ nvalid_out) {
+                       const float* __restrict__ pack, float* __restrict__ rgb_out, int32_t* __restrict__ nvalid_out, int lockstep) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __half* sW = reinterpret_cast<__half*>(smem_raw);
   float* sB = reinterpret_cast<float*>(sW + H_TOTAL);
@@ -225,7 +228,16 @@ render_blend_tc_kernel(o2345_points src, int64_t n, const uint8_t* __restrict__ 
   const int V = views.V, H = views.H, W = views.W;
   const float abs_s = sB[F_S];
 
-  for (int64_t gi = (int64_t)blockIdx.x * TW + warp; gi < n; gi += (int64_t)gridDim.x * TW) {
+  // The per-sample path is ~4 600 straight-line warp instructions (73 KB of SASS): ten warps at ten different places of it
+  // starve on instruction fetch (ncu: no_instruction = 4.5 stall cycles per issue).  lockstep: the warps of a CTA start every
+  // sample together (one barrier per ~4 600 instructions), so that they walk the code within a few cache lines of each other
+  // and share the fetches: 10.47 -> 8.74 ms per 8 192 rays with two CTAs of ten warps, 8.53 ms with ONE CTA of twenty warps per
+  // SM.  (Two more meeting points inside the sample -- before pass A and before pass B, early-leaving warps arriving without
+  // waiting -- gave nothing: 8.71 ms.)
+  for (int64_t g0 = (int64_t)blockIdx.x * TW; g0 < n; g0 += (int64_t)gridDim.x * TW) {
+    if (lockstep) __syncthreads();
+    const int64_t gi = g0 + warp;
+    if (gi >= n) continue;
     if (active && active[gi] == 0) {  // weight of this sample is exactly 0 in the compositing
       if (lane < 3) rgb_out[3 * gi + lane] = 0.f;
       if (lane == 0 && nvalid_out) nvalid_out[gi] = 0;
@@ -544,13 +556,27 @@ int launch_render_blend_tc(const o2345_points* src, int64_t n, const uint8_t* ac
                            const float* rnet_pack, float* rgb, int32_t* nvalid, cudaStream_t st) {
   static PerDeviceOnce attr_done;
   if (attr_done.need()) {
-    O2345_CUDA(cudaFuncSetAttribute(render_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    O2345_CUDA(cudaFuncSetAttribute(render_blend_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem(10)));
+    O2345_CUDA(cudaFuncSetAttribute(render_blend_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem(20)));
   }
-  int64_t need = (n + TW - 1) / TW;
-  int64_t cap = 2 * (int64_t)sm_count();
-  int grid = (int)(need < cap ? need : cap);
-  render_blend_tc_kernel<<<grid, TW * 32, TC_SMEM, st>>>(*src, n, active, vol_cl, occ, D, *views, dir_mode, query_center, dirs,
-                                                        rnet_pack, rgb, nvalid);
+  // tuning knobs (tools/time_render.py): O2345_BLEND_LOCKSTEP=0 lets the warps of a CTA drift apart, O2345_BLEND_WARPS=10 runs
+  // two CTAs of ten warps per SM (the round-1 configuration)
+  static int lockstep = -1, tw = 20;
+  if (lockstep < 0) {
+    const char* e = getenv("O2345_BLEND_LOCKSTEP");
+    lockstep = e ? atoi(e) : 1;
+    const char* w = getenv("O2345_BLEND_WARPS");
+    if (w && atoi(w) == 10) tw = 10;
+  }
+  const int64_t need = (n + tw - 1) / tw;
+  const int64_t cap = (int64_t)(20 / tw) * sm_count();
+  const int grid = (int)(need < cap ? need : cap);
+  if (tw == 20)
+    render_blend_tc_kernel<20><<<grid, 20 * 32, tc_smem(20), st>>>(*src, n, active, vol_cl, occ, D, *views, dir_mode, query_center, dirs,
+                                                                rnet_pack, rgb, nvalid, lockstep);
+  else
+    render_blend_tc_kernel<10><<<grid, 10 * 32, tc_smem(10), st>>>(*src, n, active, vol_cl, occ, D, *views, dir_mode, query_center, dirs,
+                                                                rnet_pack, rgb, nvalid, lockstep);
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }
