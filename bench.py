@@ -178,6 +178,11 @@ def run_gpu(args):
     extras["rays"]["image_ms"] = img_ms
     extras["rays"]["value"] = world * N_RAYS / (img_ms * 1e-3) / 1e6
     extras["rays"]["n_gpus"] = world
+    # the extras above ran other kernels and allocated / freed gigabytes (eager PyTorch UNet, 256^3 grids): one more untimed
+    # step brings the allocator and the caches back to the steady state the timed steps are meant to measure
+    w = time.perf_counter()
+    step()
+    beat("settling step after the extras: %.2f s" % (time.perf_counter() - w))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
