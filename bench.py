@@ -56,8 +56,9 @@ FLOP_SDF_FWD = 2 * 41856.0
 FLOP_SDF_BWD = 2 * (128 * 144 + 128 * 39)
 RAY_FLOP, RAY_GATHER_BYTES = 211e6, 4.0e6
 # ncu dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one eager UNet forward, by batch (profiles/)
-GEMM_DRAM_BYTES_PER_ITERATION = {8: 2620.6e6}
-GEMM_DRAM_NOTE = "ncu launch list of one UNet iteration (profiles/r2_unet_launches_summary.txt); algorithmic: 1.72 GB of fp16 weights + activations"
+GEMM_DRAM_BYTES_PER_ITERATION = {8: 2620.6e6, 16: 3751.0e6, 64: 16047.4e6}
+GEMM_DRAM_NOTE = ("ncu launch lists of one eager UNet iteration per batch (profiles/r2_unet_b64_launches_summary.txt, "
+                  "r2_unet_launches_summary.txt): a committed measurement, ncu cannot run inside the bench")
 PUBLISHED_SEC_PER_MESH = 40.0   # BASELINE.md section 1 (reference README.md:154, A6000, whole run.py)
 
 
@@ -296,14 +297,21 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
             for n in real:
                 setattr(ops_a, n, real[n])
             unet.use_cuda_graph = True
-        flops_counted = 0.0
+        flops_counted, algo_bytes = 0.0, 0.0
         for name, a, k in rec:
+            res = 2.0 if k.get("residual") is not None else 0.0
             if name == "gemm":
-                flops_counted += 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
+                M, K, N = a[0].shape[0], a[0].shape[1], a[1].shape[0]
+                n_out = N // 2 if k.get("act", 0) == ops_a.ACT_GEGLU else N
+                flops_counted += 2.0 * M * K * N
+                algo_bytes += 2.0 * (M * K + N * K) + (2.0 + res) * M * n_out
             elif name == "conv3x3":
-                flops_counted += 2.0 * a[1] * a[2] * a[3] * 9 * a[4] * a[5].shape[0]
+                M, C, N = a[1] * a[2] * a[3], a[4], a[5].shape[0]
+                flops_counted += 2.0 * M * 9 * C * N
+                algo_bytes += 2.0 * (M * C + N * 9 * C) + (2.0 + res) * M * N          # the activation is read once, not nine times
             else:
                 flops_counted += 2.0 * a[3] * a[4] * a[8] * a[9] * a[10]
+                algo_bytes += 2.0 * a[3] * a[4] * (a[8] * a[10] + a[9] * a[10] + a[8] * a[9])
         side = torch.cuda.Stream()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.stream(side):
@@ -320,11 +328,11 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
         del graph, rec
         beat("stage breakdown: UNet iteration at batch %d: %.3f ms; its %d GEMM launches replay in %.3f ms (%.0f TFLOP/s)"
              % (B, ms_unet, n, ms_gemm, flops_counted / ms_gemm / 1e9))
-        return ms_unet, ms_gemm, flops_counted, n, (x, t, ctx)
+        return ms_unet, ms_gemm, flops_counted, n, (x, t, ctx), algo_bytes
 
     prof = {B: unet_profile(B) for B, _ in UNET_SCHEDULE}
     B_TOP = max(UNET_SCHEDULE, key=lambda bi: prof[bi[0]][0] * bi[1])[0]       # the batch whose iterations take the larger share
-    ms_unet, ms_gemm, flops_counted, n_gemm, (x, t, ctx) = prof[B_TOP]
+    ms_unet, ms_gemm, flops_counted, n_gemm, (x, t, ctx), algo_bytes = prof[B_TOP]
     # informational (SURVEY.md 2a "beats PyTorch / cuDNN on the same box"): the plain-PyTorch restatement of the same UNet
     # (oracle/ldm_oracle.py: F.conv2d / F.linear / einsum attention -> cuDNN + cuBLAS) under fp16 autocast on this GPU, eager,
     # outside every timed region, at the same batch.  It is the reference's execution model, not the product path.
@@ -356,7 +364,7 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
                 "bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
                 "traffic": GEMM_DRAM_BYTES_PER_ITERATION.get(B_TOP, 0.0) / max(n_gemm, 1) or None,
                 "traffic_unit": "bytes of DRAM traffic per launch (mean)",
-                "traffic_note": GEMM_DRAM_NOTE,
+                "traffic_note": GEMM_DRAM_NOTE, "algorithmic_bytes_per_launch": algo_bytes / max(n_gemm, 1),
                 "flops_per_step": flops_counted, "gemm_ms_per_unet_iteration": ms_gemm,
                 "other_batches": {str(B): {"unet_iteration_ms": prof[B][0], "gemm_ms": prof[B][1],
                                            "tflops": prof[B][2] / (prof[B][1] * 1e-3) / 1e12} for B, _ in UNET_SCHEDULE if B != B_TOP},

@@ -119,28 +119,35 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
         mma16816(s[j + 1], qa[kk], b2, b3);
       }
     }
-    // ---- online softmax (rows g and g+8 of this warp's tile), base-2 exponent with the scale folded in
+    // ---- online softmax (rows g and g+8 of this warp's tile).  The running maximum is kept on the RAW scores; the scale
+    // (softmax scale x log2 e, > 0) is folded into the exponent: p = 2^(s * c - m * c) is one FFMA + one ex2 per score (round 2
+    // first scaled every score, then subtracted: two instructions more per score in the loop that bounds this kernel).  Keys
+    // past N only exist in the last tile: the masking compare / select runs there only.
+    if (k0 + KT > N) {
+#pragma unroll
+      for (int j = 0; j < KT / 8; ++j) {
+        const int key = k0 + 8 * j + 2 * t;
+        if (key >= N) s[j][0] = -1e30f, s[j][2] = -1e30f;
+        if (key + 1 >= N) s[j][1] = -1e30f, s[j][3] = -1e30f;
+      }
+    }
     float mx0 = -1e30f, mx1 = -1e30f;
 #pragma unroll
     for (int j = 0; j < KT / 8; ++j) {
-      int key = k0 + 8 * j + 2 * t;
-      s[j][0] = key < N ? s[j][0] * scale_log2 : -1e30f;
-      s[j][1] = key + 1 < N ? s[j][1] * scale_log2 : -1e30f;
-      s[j][2] = key < N ? s[j][2] * scale_log2 : -1e30f;
-      s[j][3] = key + 1 < N ? s[j][3] * scale_log2 : -1e30f;
       mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
       mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    float a0 = ex2(m0 - mn0), a1 = ex2(m1 - mn1);
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = ex2((m0 - mn0) * scale_log2), a1 = ex2((m1 - mn1) * scale_log2);
     m0 = mn0, m1 = mn1;
+    const float ms0 = -mn0 * scale_log2, ms1 = -mn1 * scale_log2;
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int j = 0; j < KT / 8; ++j) {
-      s[j][0] = ex2(s[j][0] - mn0), s[j][1] = ex2(s[j][1] - mn0);
-      s[j][2] = ex2(s[j][2] - mn1), s[j][3] = ex2(s[j][3] - mn1);
+      s[j][0] = ex2(fmaf(s[j][0], scale_log2, ms0)), s[j][1] = ex2(fmaf(s[j][1], scale_log2, ms0));
+      s[j][2] = ex2(fmaf(s[j][2], scale_log2, ms1)), s[j][3] = ex2(fmaf(s[j][3], scale_log2, ms1));
       r0 += s[j][0] + s[j][1], r1 += s[j][2] + s[j][3];
     }
     l0 = l0 * a0 + r0, l1 = l1 * a1 + r1;

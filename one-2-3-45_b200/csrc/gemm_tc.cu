@@ -1183,10 +1183,11 @@ Config pick_config(const GemmParams& p, int nk, bool can_split, int64_t ws_float
   // with long K it LOSES (65536 x 320 x 2880 conv 111 -> 141 us): one CTA per SM keeps 128-156 KB of operands in flight
   // against 192-208 KB for two resident per-tile CTAs, and the main loop is bound by bytes in flight.
   if (g_persist == 0 && g_force[0] == 0 && g_force[1] == 0 && g_force[2] == 0 && !p.out_f32 && nk <= 20) {
-    const int bn_p = N >= 512 ? 256 : 160;
+    // tile width: 256 where it divides the work well, 160 for the UNet's N = 320 / 640 / 960, 128 for N = 128 (the VAE's top level)
+    const int bn_p = (N >= 512 || N == 256) ? 256 : ((N % 160) == 0 || N > 128) ? 160 : 128;
     const int tiles = cdiv(M, 2 * BM) * cdiv(N, bn_p);
     const int min_tiles = g_persist_min_tiles > 0 ? g_persist_min_tiles : sm_count() / 2;
-    if (tiles >= min_tiles && (N >= 512 || nk >= 8)) c.ctas = 2, c.bn = bn_p, c.splits = 1, c.persist = 1;
+    if (N >= 128 && tiles >= min_tiles && (N >= 512 || nk >= 8)) c.ctas = 2, c.bn = bn_p, c.splits = 1, c.persist = 1;
   }
   return c;
 }

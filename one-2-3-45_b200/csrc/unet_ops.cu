@@ -136,6 +136,52 @@ __global__ void norm_act_im2col_kernel(const __half* __restrict__ x, int B, int 
   *reinterpret_cast<uint4*>(out + (pix * KS * KS + kk) * C + cc * 8) = o;
 }
 
+// KS = 1 without stride / up-sampling is a plain per-(image, channel) affine (+SiLU) over the activation -- most GroupNorm
+// applications of the VAE, whose maps are too large for the one-kernel cluster GroupNorm.  grid (chunks, B); blockDim is a
+// multiple of C / 8, so a thread keeps its 8-channel slot (scale / shift fetched once, no index divisions per element) and
+// has four 16-byte loads in flight.  (The general gather above spends ~300 instructions per 16 bytes on 64-bit index
+// arithmetic and table loads: 1.3 TB/s on the VAE's 67 MB maps.)
+__global__ void norm_act_apply_kernel(const __half* __restrict__ x, int HW, int C, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, int act, __half* __restrict__ out, int P) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int U = 4;
+  const int b = blockIdx.y, c8n = C >> 3;
+  const int slot = threadIdx.x % c8n, prow = threadIdx.x / c8n, rows = blockDim.x / c8n;
+  float sv[8], tv[8];
+  {
+    const float4* sc = reinterpret_cast<const float4*>(scale + (int64_t)b * C + slot * 8);
+    const float4* sh = reinterpret_cast<const float4*>(shift + (int64_t)b * C + slot * 8);
+    const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), t0 = __ldg(sh), t1 = __ldg(sh + 1);
+    sv[0] = s0.x, sv[1] = s0.y, sv[2] = s0.z, sv[3] = s0.w, sv[4] = s1.x, sv[5] = s1.y, sv[6] = s1.z, sv[7] = s1.w;
+    tv[0] = t0.x, tv[1] = t0.y, tv[2] = t0.z, tv[3] = t0.w, tv[4] = t1.x, tv[5] = t1.y, tv[6] = t1.z, tv[7] = t1.w;
+  }
+  const int p0 = blockIdx.x * P, p1 = min(HW, p0 + P);
+  const __half* base = x + (int64_t)b * HW * C + slot * 8;
+  __half* obase = out + (int64_t)b * HW * C + slot * 8;
+  for (int pix = p0 + prow; pix < p1; pix += U * rows) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (pix + u * rows < p1) v[u] = *reinterpret_cast<const uint4*>(base + (int64_t)(pix + u * rows) * C);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pu = pix + u * rows;
+      if (pu >= p1) break;
+      const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+      __half2 r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h[e]);
+        f.x = fmaf(f.x, sv[2 * e], tv[2 * e]), f.y = fmaf(f.y, sv[2 * e + 1], tv[2 * e + 1]);
+        if (act) f.x = silu(f.x), f.y = silu(f.y);
+        r[e] = __floats2half2_rn(f.x, f.y);
+      }
+      *reinterpret_cast<uint4*>(obase + (int64_t)pu * C) = *reinterpret_cast<uint4*>(r);
+    }
+  }
+}
+
 // The same gather with the GroupNorm finished IN the consumer: instead of a scale / shift table it receives the raw per-(image,
 // channel) sums and sums of squares that the PRODUCING GEMM accumulated in its epilogue (o2345_epilogue.colstats) -- for a
 // channel concat, one table per part -- and turns them into mean / rstd per group in its prologue: no kernel re-reads the
@@ -619,6 +665,17 @@ extern "C" int o2345_norm_act_im2col(const void* x, int B, int H, int W, int C, 
   int Hin = upsample ? 2 * H : H, Win = upsample ? 2 * W : W;
   int pad_hi = ksize / 2, pad = pad_lo < 0 ? ksize / 2 : pad_lo;   // pad_lo = 0: the VAE's (0,1,0,1) down-sampling pad
   int Ho = (Hin + pad + pad_hi - ksize) / stride + 1, Wo = (Win + pad + pad_hi - ksize) / stride + 1;
+  if (ksize == 1 && stride == 1 && !upsample && scale && C / 8 <= 512 && (int64_t)H * W < (1 << 30)) {
+    const int c8 = C / 8, threads = (512 / c8) * c8, rows = threads / c8, HW = H * W;
+    int chunks = cdiv(4 * sm_count(), B);
+    if (chunks > HW / (4 * rows)) chunks = HW / (4 * rows);
+    if (chunks < 1) chunks = 1;
+    const int P = cdiv(HW, chunks);
+    O2345_CUDA(launch_pdl(norm_act_apply_kernel, dim3(cdiv(HW, P), B), dim3(threads), (size_t)(0), ST, (const __half*)x, HW, C, scale, shift, act,
+                          (__half*)out, P));
+    O2345_LAUNCH_CHECK();
+    return O2345_OK;
+  }
   int64_t total = (int64_t)B * Ho * Wo * ksize * ksize * (C / 8);
   O2345_CUDA(launch_pdl(norm_act_im2col_kernel, dim3(cdiv(total, 256)), dim3(256), (size_t)(0), ST, (const __half*)x, B, H, W, C, ksize, stride, upsample, scale, shift,
                                                            act, (__half*)out, Ho, Wo, pad));
