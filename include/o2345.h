@@ -326,6 +326,16 @@ void o2345_debug_gemm_trace(long long* device_buf16);
 int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
                       const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
 
+/* Nearest-neighbour 2x up-sampling followed by a 3x3 convolution (zero padding 1) -- the Upsample layers of the UNet and the
+ * VAE decoder (reference ldm/modules/diffusionmodules/openaimodel.py:118-129 `Upsample.forward`, model.py:43-53) -- WITHOUT
+ * materialising the up-sampled map or a patch matrix: every output pixel (2y+a, 2x+b) sees the 3x3 kernel collapse onto a
+ * 2x2 window of the low-resolution input, so the layer is four 2x2 implicit convolutions, one per phase (a, b).
+ * x [B, H, W, C] channel-last fp16 (the LOW-resolution map, same tiling rule as o2345_conv3x3_f16); weight4 [4][N][4*C] fp16:
+ * phase 2a+b, taps in (ty, tx, c) order with the collapsed kernel rows / columns summed (a = 0: {k0, k1+k2}, a = 1: {k0+k1, k2});
+ * out [B*2H*2W, ldc] fp16.  Epilogue: bias / activation only. */
+int o2345_conv_up2x_f16(const void* x, int B, int H, int W, int C, const void* weight4, int N, void* out, int64_t ldc,
+                        const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Path A glue (rows A1, A3, A4, A6): channel-last fp16 activations [B, H*W, C]; fp32 statistics.
  * GroupNorm32 / SiLU / conv patch gather: ldm/modules/diffusionmodules/openaimodel.py:92-161,256-276,

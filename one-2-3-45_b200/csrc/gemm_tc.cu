@@ -192,6 +192,12 @@ struct GemmParams {
   // 4-D tensor map (C, W, H, B); an output tile of 128 consecutive pixels is a box (64 ch, tw, th, tb), and kernel tap
   // (ky, kx) is the same box shifted by (kx-1, ky-1) -- TMA's out-of-bounds zero fill IS the convolution padding.
   int conv, cC, cH, cW, cblocks;
+  // tap geometry: ctaps taps in rows of ctx, tap j reads the box shifted by (j % ctx + cox, j / ctx + coy).  3 x 3 / pad 1: ctaps 9,
+  // ctx 3, cox = coy = -1.  Nearest-neighbour 2x up-sampling followed by a 3 x 3 convolution is FOUR 2 x 2 convolutions of the
+  // low-resolution input, one per output phase (a, b) = (row parity, column parity): ctaps 4, ctx 2, cox = b - 1, coy = a - 1,
+  // weights pre-summed on the host (rows that collapse onto the same input pixel), and the tile's 128 low-resolution pixels
+  // are written to output pixels (2 y + a, 2 x + b): up = 1, upa = a, upb = b.  No im2col buffer, 4 C instead of 9 C per output.
+  int ctaps, ctx, cox, coy, up, upa, upb;
   // split-K: the splits of a tile form one cluster; CTA z stores its partial accumulator in plane z of ws [splits, M, N],
   // the cluster barrier publishes the planes, then every split sums and finishes its share of the tile.
   int splits;
@@ -211,6 +217,13 @@ __device__ __forceinline__ void stamp(const GemmParams& p, int slot) {
 // wall-clock (globaltimer, ns) stamps of tile (0,0): comparable across the SMs the splits of a tile run on
 __device__ __forceinline__ void stamp_ns(const GemmParams& p, int slot, bool any_z = false) {
   if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (any_z || blockIdx.z == 0)) p.trace[slot] = (long long)global_ns();
+}
+
+// row of C that accumulator row `row` is written to (up-sampling phases scatter the low-resolution pixels over the 2x grid)
+__device__ __forceinline__ int64_t out_row(const GemmParams& p, int row) {
+  if (!p.up) return row;
+  const int x = row % p.cW, t = row / p.cW, y = t % p.cH, b = t / p.cH;
+  return ((int64_t)b * (2 * p.cH) + 2 * y + p.upa) * (2 * p.cW) + 2 * x + p.upb;
 }
 
 __device__ __noinline__ void wait_timed_out(const GemmParams& p, int tag, int stage) {
@@ -381,7 +394,7 @@ __device__ __forceinline__ void splitk_finalize(const GemmParams& p, int m0, int
     for (int i = z * share + te; i < i1; i += EPI_THREADS) {
       const int rl = i / PPR, row = m0 + rl, col = n0 + (i - rl * PPR) * 8;
       if (row >= p.M || col >= p.N) continue;
-      const int64_t woff = (int64_t)row * p.N + col, o = (int64_t)row * p.ldc + col;
+      const int64_t woff = (int64_t)row * p.N + col, o = out_row(p, row) * p.ldc + col;
       uint4 qb = make_uint4(0u, 0u, 0u, 0u), qr = make_uint4(0u, 0u, 0u, 0u);
       if (p.rowbias) qb = *reinterpret_cast<const uint4*>(p.rowbias + (int64_t)(row / p.rows_per_group) * p.rowbias_ld + col);
       if (p.residual) qr = *reinterpret_cast<const uint4*>(p.residual + o);
@@ -451,7 +464,7 @@ __device__ __forceinline__ void splitk_finalize(const GemmParams& p, int m0, int
     if (p.rowbias) x += __half2float(p.rowbias[(int64_t)(row / p.rows_per_group) * p.rowbias_ld + col]);
     if (p.bias) x += __ldg(p.bias + col);
     x = apply_act(x, p.act);
-    const int64_t o = (int64_t)row * p.ldc + col;
+    const int64_t o = out_row(p, row) * p.ldc + col;
     if (p.residual) x += __half2float(p.residual[o]);
     if (p.out_f32) reinterpret_cast<float*>(p.C)[o] = x;
     else reinterpret_cast<__half*>(p.C)[o] = __float2half_rn(x);
@@ -563,7 +576,7 @@ __device__ __forceinline__ void prefetch_residual(const GemmParams& p, const War
     if (p.residual && pp < g.total) {
       const int rl = pp / g.ppr, ci = pp - rl * g.ppr;
       const int grow = row0 + rl, col = g.ocol0 + ci * 8;
-      if (grow < p.M && col < g.nout) resq[u] = *reinterpret_cast<const uint4*>(p.residual + (int64_t)grow * p.ldc + col);
+      if (grow < p.M && col < g.nout) resq[u] = *reinterpret_cast<const uint4*>(p.residual + out_row(p, grow) * p.ldc + col);
     }
   }
 }
@@ -631,7 +644,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const WarpO
           v = add_h8(v, resq[u]);
           if (p.colstats) *reinterpret_cast<uint4*>(slab + rl * g.stride + ci * 16) = v;   // the statistics see the final value
         }
-        *reinterpret_cast<uint4*>(C + (int64_t)grow * p.ldc + col) = v;
+        *reinterpret_cast<uint4*>(C + out_row(p, grow) * p.ldc + col) = v;
       }
     }
   }
@@ -646,7 +659,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const WarpO
       const int rl = pp / g.ppr, ci = pp - rl * g.ppr;
       const int grow = row0 + rl, col = g.ocol0 + ci * 8;
       ok[u] = pp < g.total && grow < p.M && col < g.nout;
-      o[u] = (int64_t)grow * p.ldc + col;
+      o[u] = out_row(p, grow) * p.ldc + col;
       if (ok[u]) {
         v[u] = *reinterpret_cast<const uint4*>(slab + rl * g.stride + ci * 16);
         if (p.residual) q[u] = *reinterpret_cast<const uint4*>(p.residual + o[u]);
@@ -715,7 +728,7 @@ __device__ __forceinline__ void produce_stage(const GemmParams& p, const CUtenso
     if (p.conv) {
       const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
       const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
-      tma2_load_4d(a_dst, tmA, full_bar, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+      tma2_load_4d(a_dst, tmA, full_bar, c0, x0 + tap % p.ctx + p.cox, y0 + tap / p.ctx + p.coy, b0);
       tma2_load_2d(b_dst, tmB, full_bar, tap * p.cC + c0, nb);
     } else {
       tma2_load_2d(a_dst, tmA, full_bar, kb * BK, m0);
@@ -726,7 +739,7 @@ __device__ __forceinline__ void produce_stage(const GemmParams& p, const CUtenso
     if (p.conv) {
       const int tap = kb / p.cblocks, c0 = (kb - tap * p.cblocks) * BK;
       const int x0 = m0 % p.cW, y0 = (m0 / p.cW) % p.cH, b0 = m0 / (p.cW * p.cH);
-      tma_load_4d(a_dst, tmA, full_bar, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+      tma_load_4d(a_dst, tmA, full_bar, c0, x0 + tap % p.ctx + p.cox, y0 + tap / p.ctx + p.coy, b0);
       tma_load_2d(b_dst, tmB, full_bar, tap * p.cC + c0, n0);
     } else if (p.batched) {
       tma_load_4d(a_dst, tmA, full_bar, kb * BK, m0, bz % p.nh, bz / p.nh);
@@ -773,7 +786,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1u));
   const int m0 = CTAS == 2 ? (blockIdx.x >> 1) * (2 * BM) + (int)rank * BM : blockIdx.x * BM;
   const int n0 = blockIdx.y * BN, bz = blockIdx.z;
-  const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
+  const int nk = p.conv ? p.ctaps * p.cblocks : (p.K + BK - 1) / BK;
   // split-K: blockIdx.z owns k-blocks [kb0, kb1) and adds its partial tile into the fp32 workspace
   int kb0 = 0, kb1 = nk;
   if (MODE == 3 && p.splits > 1) {
@@ -867,7 +880,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (te == 0) stamp_ns(p, 18);
       } else {
         const int64_t crow = (p.batched ? (int64_t)(bz % p.nh) * p.stride_c_h + (int64_t)(bz / p.nh) * p.stride_c_b : 0) +
-                             (int64_t)row * p.ldc;
+                             out_row(p, row < p.M ? row : 0) * p.ldc;
 #pragma unroll 1
         for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
           uint32_t r[32];
@@ -949,7 +962,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int ntiles = ((p.M + 2 * BM - 1) / (2 * BM)) * tiles_n;
-  const int nk = p.conv ? 9 * p.cblocks : (p.K + BK - 1) / BK;
+  const int nk = p.conv ? p.ctaps * p.cblocks : (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -1350,19 +1363,12 @@ extern "C" int o2345_last_trap(char* buf, size_t n) {
   return 1;
 }
 
-extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
-                                 const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream) {
-  O2345_CHECK_ARG(x && weight && out, "null pointer");
-  O2345_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0 && N > 0, "bad sizes (C must be a multiple of 8)");
-  // an output tile is 128 consecutive pixels fetched as ONE box (tw, th, tb): either whole multiples of 128 along a row,
-  // or whole rows that tile the image exactly (H a multiple of 128 / W), or whole images (H * W divides 128).  Any other
-  // shape would wrap a tile across the image border (silently wrong rows) or give a box of fewer than 128 rows (the
-  // stage's byte count would never be reached): refused here, callers take the im2col route.
-  O2345_CHECK_ARG((W % 128) == 0 || ((128 % W) == 0 && (((int64_t)H * W >= 128 && (H % (128 / W)) == 0) ||
-                                                        ((int64_t)H * W < 128 && (128 % (H * W)) == 0))),
-                  "implicit 3x3 conv: the image must tile into 128-pixel boxes (W % 128 == 0, or 128 % W == 0 with "
-                  "H % (128 / W) == 0, or 128 % (H * W) == 0)");
-  O2345_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)weight % 16) == 0, "operands must be 16-byte aligned");
+namespace o2345 {
+namespace {
+// One implicit convolution launch over the channel-last activation x [B, H, W, C]: `taps` taps in rows of `tx`, tap j shifted by
+// (j % tx + ox, j / tx + oy); weight [N, taps * C] in (tap, channel) order; up / upa / upb: see GemmParams.
+int conv_launch(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc, const o2345_epilogue* ep,
+                float* splitk_ws, int64_t ws_floats, int taps, int tx, int ox, int oy, int up, int upa, int upb, cudaStream_t st) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return O2345_ECUDA; }
   const int tw = W >= 128 ? 128 : W;
@@ -1380,17 +1386,57 @@ extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, cons
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (conv activation) failed with %d", (int)r); return O2345_ECUDA; }
   }
   GemmParams p;
-  p.M = B * H * W, p.N = N, p.K = 9 * C, p.ldc = ldc, p.nh = 1, p.stride_c_h = 0, p.stride_c_b = 0, p.C = out;
+  p.M = B * H * W, p.N = N, p.K = taps * C, p.ldc = ldc, p.nh = 1, p.stride_c_h = 0, p.stride_c_b = 0, p.C = out;
   int rc = fill_epilogue(p, ep, p.M, N, ldc);
   if (rc) return rc;
   p.batched = 0, p.conv = 1, p.cC = C, p.cH = H, p.cW = W, p.cblocks = (C + BK - 1) / BK;
+  p.ctaps = taps, p.ctx = tx, p.cox = ox, p.coy = oy, p.up = up, p.upa = upa, p.upb = upb;
   set_workspace(p, splitk_ws, ws_floats);
-  cudaStream_t st = (cudaStream_t)stream;
-  const Config c = pick_config(p, 9 * p.cblocks, true, ws_floats);
+  const Config c = pick_config(p, taps * p.cblocks, true, ws_floats);
   p.splits = c.splits;
-  rc = make_map(&mb, weight, N, 9 * (int64_t)C, 9 * (int64_t)C, 0, 0, 0, 0, c.bn / c.ctas);
+  rc = make_map(&mb, weight, N, taps * (int64_t)C, taps * (int64_t)C, 0, 0, 0, 0, c.bn / c.ctas);
   if (rc) return rc;
   return dispatch(c, pick_mode(p, c), ma, mb, p, 0, st);
+}
+
+// an output tile is 128 consecutive pixels fetched as ONE box (tw, th, tb): either whole multiples of 128 along a row,
+// or whole rows that tile the image exactly (H a multiple of 128 / W), or whole images (H * W divides 128).  Any other
+// shape would wrap a tile across the image border (silently wrong rows) or give a box of fewer than 128 rows (the
+// stage's byte count would never be reached): refused, callers take the im2col route.
+bool conv_tiles(int H, int W) {
+  return (W % 128) == 0 || ((128 % W) == 0 && (((int64_t)H * W >= 128 && (H % (128 / W)) == 0) || ((int64_t)H * W < 128 && (128 % (H * W)) == 0)));
+}
+}  // namespace
+}  // namespace o2345
+
+extern "C" int o2345_conv3x3_f16(const void* x, int B, int H, int W, int C, const void* weight, int N, void* out, int64_t ldc,
+                                 const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && weight && out, "null pointer");
+  O2345_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0 && N > 0, "bad sizes (C must be a multiple of 8)");
+  O2345_CHECK_ARG(conv_tiles(H, W),
+                  "implicit 3x3 conv: the image must tile into 128-pixel boxes (W % 128 == 0, or 128 % W == 0 with "
+                  "H % (128 / W) == 0, or 128 % (H * W) == 0)");
+  O2345_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)weight % 16) == 0, "operands must be 16-byte aligned");
+  return conv_launch(x, B, H, W, C, weight, N, out, ldc, ep, splitk_ws, ws_floats, 9, 3, -1, -1, 0, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int o2345_conv_up2x_f16(const void* x, int B, int H, int W, int C, const void* weight4, int N, void* out, int64_t ldc,
+                                   const o2345_epilogue* ep, float* splitk_ws, int64_t ws_floats, o2345_stream_t stream) {
+  O2345_CHECK_ARG(x && weight4 && out, "null pointer");
+  O2345_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0 && N > 0, "bad sizes (C must be a multiple of 8)");
+  O2345_CHECK_ARG(conv_tiles(H, W), "up-sampling conv: the LOW-resolution image must tile into 128-pixel boxes (see o2345_conv3x3_f16)");
+  O2345_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)weight4 % 16) == 0, "operands must be 16-byte aligned");
+  O2345_CHECK_ARG(!ep || (!ep->residual && !ep->colstats && !ep->rowbias && ep->act != 3),
+                  "up-sampling conv: bias / activation epilogues only (no residual, row bias, statistics, GEGLU)");
+  O2345_CHECK_ARG((int64_t)B * 4 * H * W < (1ll << 31), "output rows must fit 31 bits");
+  const __half* w = reinterpret_cast<const __half*>(weight4);
+  for (int ph = 0; ph < 4; ++ph) {   // phase (a, b) = (row parity, column parity) of the output pixel
+    const int a = ph >> 1, b = ph & 1;
+    int rc = conv_launch(x, B, H, W, C, w + (int64_t)ph * N * 4 * C, N, out, ldc, ep, splitk_ws, ws_floats, 4, 2, b - 1, a - 1, 1, a, b,
+                         (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return O2345_OK;
 }
 
 extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int N, int K, int64_t lda, int64_t ldb,
@@ -1410,6 +1456,7 @@ extern "C" int o2345_gemm_f16(const void* A, const void* B, void* C, int M, int 
   O2345_CHECK_ARG(nh == 0 || (!p.rowbias && p.act != 3), "row bias / GEGLU are not available in batched mode");
   p.batched = nh > 0 ? 1 : 0;
   p.conv = 0, p.cC = p.cH = p.cW = p.cblocks = 0;
+  p.ctaps = p.ctx = p.cox = p.coy = p.up = p.upa = p.upb = 0;
   set_workspace(p, splitk_ws, ws_floats);
   cudaStream_t st = (cudaStream_t)stream;
   const Config c = pick_config(p, cdiv(K, BK), nh == 0, ws_floats);

@@ -89,6 +89,8 @@ _SIGS = {
     "o2345_last_trap": (C.c_int, [C.c_char_p, C.c_size_t]),
     "o2345_conv3x3_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64,
                                     C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
+    "o2345_conv_up2x_f16": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_i64,
+                                      C.POINTER(Epilogue), c_fp, c_i64, c_fp]),
     "o2345_groupnorm_scratch_floats": (c_i64, [C.c_int, C.c_int]),
     "o2345_groupnorm_stats": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_fp, c_fp, c_fp, c_fp, c_fp,
                                         c_fp]),

@@ -134,6 +134,9 @@ class AutoencoderKL(nn.Module):
         if ksize == 3 and stride == 1 and not up and pad_lo < 0 and A.conv3x3_supported(H, W, C):
             a = x if g is None else A.norm_act_im2col(x, B, H, W, C, 1, 1, False, g, True)[0]
             return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual), H, W
+        if A.USE_CONV_UP2X and ksize == 3 and stride == 1 and up and g is None and residual is None and pad_lo < 0 and A.conv3x3_supported(H, W, C):
+            w4, b4 = pk.conv_up(conv)       # nearest 2x + 3x3 conv as four 2x2 convs of the low-resolution map
+            return A.conv_up2x(x, B, H, W, C, w4, bias=b4), 2 * H, 2 * W
         a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, ksize, stride, up, g, gn is not None and ksize == 3, pad_lo=pad_lo)
         return A.gemm(a, w, bias=b, residual=residual), Ho, Wo
 

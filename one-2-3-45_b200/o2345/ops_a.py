@@ -233,6 +233,20 @@ def attention(q, k, v, B, N, H, d, out=None):
     return out
 
 
+USE_CONV_UP2X = True   # tools/unet_ab.py switches the four-phase up-sampling convolution off to measure the gather route
+
+
+def conv_up2x(x, B, H, W, C, weight4, bias=None, act=0):
+    """Nearest-neighbour 2x up-sampling followed by a 3x3 convolution (pad 1) of the channel-last x [B*H*W, C], as four 2x2
+    convolutions of the LOW-resolution map (weight4 [4, N, 4*C] from _Packed.conv_up).  -> [B*2H*2W, N] fp16."""
+    N = weight4.shape[1]
+    assert weight4.shape == (4, N, 4 * C) and weight4.dtype == _f16 and weight4.is_contiguous()
+    out = torch.empty(B * 4 * H * W, N, dtype=_f16, device=x.device)
+    ep = _epilogue(bias, None, None, 1, act, 1.0, False, None)
+    L.call("o2345_conv_up2x_f16", _v(x), B, H, W, C, _v(weight4), N, _v(out), N, C_.byref(ep), _v(_splitk_ws(x.device)), WS_FLOATS, _stream())
+    return out
+
+
 def conv3x3(x, B, H, W, C, weight, bias=None, residual=None, act=0, out_dtype=_f16, rowbias=None, colstats=None):
     """Implicit-GEMM 3x3 convolution (stride 1, pad 1) of a channel-last activation x [B*H*W, C]; weight [N, 9*C] in
     (ky, kx, c) order.  No im2col buffer: TMA fetches the nine shifted windows, zero-filling outside the image.

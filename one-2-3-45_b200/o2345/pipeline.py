@@ -67,7 +67,7 @@ def build_networks(device, vol_dim=96, states=None, n_samples=64, n_importance=6
 
 def _sample_from(cams, imgs, device, H, W, pin=False):
     """Adds the batch dimension the reference's DataLoader adds and moves everything to `device`."""
-    t = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+    t = lambda x: x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))     # device-resident views pass through
     rays_o, rays_v = S.query_rays(cams["query_intrinsic"], cams["query_c2w"], H, W)
     host = {
         "images": t(imgs[1:])[None], "query_image": t(imgs[0])[None], "w2cs": t(cams["w2cs"])[None],
@@ -79,7 +79,7 @@ def _sample_from(cams, imgs, device, H, W, pin=False):
     }
     rays = {"rays_o": t(rays_o)[None], "rays_v": t(rays_v)[None]}
     if pin:
-        host = {k: v.pin_memory() for k, v in host.items()}
+        host = {k: (v if v.is_cuda else v.pin_memory()) for k, v in host.items()}
         rays = {k: v.pin_memory() for k, v in rays.items()}
     sample = {k: v.to(device, non_blocking=pin) for k, v in host.items()}
     sample["rays"] = {k: v.to(device, non_blocking=pin) for k, v in rays.items()}
@@ -125,10 +125,12 @@ def load_sample(folder, device):
 def sample_from_views(stage1, stage2, pose, device, pin=False):
     """The batch dict of BlenderPerView built from in-memory views instead of PNG files."""
     ids = list(pose["c2ws"].keys())
-    to_f = lambda u8: (u8.astype(np.float32) / 255.0).transpose(2, 0, 1)
     first = int(ids[0].split(".")[0])
-    imgs = [to_f(stage1[first])] + [to_f(stage2[ids[v].split(".")[0]]) for v in range(8, 40)]
-    imgs = np.stack(imgs).astype(np.float32)
+    views = [stage1[first]] + [stage2[ids[v].split(".")[0]] for v in range(8, 40)]
+    if torch.is_tensor(views[0]):      # uint8 [H, W, 3] on the device (generate_views(keep_on_device=True)): the same u8 / 255 there
+        imgs = (torch.stack(views).to(torch.float32) / 255.0).permute(0, 3, 1, 2).contiguous()
+    else:
+        imgs = np.stack([(u8.astype(np.float32) / 255.0).transpose(2, 0, 1) for u8 in views]).astype(np.float32)
     H, W = imgs.shape[2:]
     cams = S.scene_cameras(pose, n_src=32, img_wh=(W, H))
     return _sample_from(cams, imgs, device, H, W, pin=pin)[0]
@@ -142,7 +144,8 @@ def image_to_mesh(zero123, trainer, input_u8, polar_angle=60, resolution=256, dd
     Returns dict(vertices, triangles, colors) as host numpy arrays (and writes mesh.ply when exp_dir is given)."""
     from .zero123 import generate_views
     dev = next(trainer.parameters()).device
-    stage1, stage2, pose = generate_views(zero123, input_u8, polar_angle, ddim_steps, stage2_steps, scale, exp_dir, dev, batched=batched)
+    stage1, stage2, pose = generate_views(zero123, input_u8, polar_angle, ddim_steps, stage2_steps, scale, exp_dir, dev, batched=batched,
+                                          keep_on_device=exp_dir is None)
     sample = sample_from_views(stage1, stage2, pose, dev)
     trainer.base_exp_dir = exp_dir
     return trainer(sample, mode="export_mesh", resolution=resolution)

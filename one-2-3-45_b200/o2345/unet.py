@@ -120,6 +120,29 @@ class _Packed:
                          None if m.bias is None else m.bias.detach().to(_f32).contiguous())
         return self.w[k]
 
+    def conv_up(self, m):
+        """Weights of `nearest 2x up-sampling -> 3x3 conv` as FOUR 2x2 convolutions of the low-resolution input, one per output
+        phase (row parity a, column parity b): the three kernel rows collapse onto two input rows -- a = 0: (row y-1: k0,
+        row y: k1 + k2), a = 1: (row y: k0 + k1, row y+1: k2) -- and the same along x.  Summed in fp32, rounded to fp16
+        once.  -> ([4, Cout, 4 * Cin] fp16 in (phase, out, (ty, tx, cin)) order, bias fp32)."""
+        k = ("up", id(m))
+        if k not in self.w:
+            w = m.weight.detach().float()                                     # [co, ci, 3, 3]
+            co, ci = w.shape[:2]
+            assert ci % 8 == 0 and w.shape[2:] == (3, 3)
+            rows = {0: (w[:, :, 0], w[:, :, 1] + w[:, :, 2]), 1: (w[:, :, 0] + w[:, :, 1], w[:, :, 2])}   # [co, ci, 3 (kx)] each
+            phases = []
+            for a in (0, 1):
+                for b in (0, 1):
+                    taps = []
+                    for ty in (0, 1):
+                        r = rows[a][ty]
+                        cols = (r[:, :, 0], r[:, :, 1] + r[:, :, 2]) if b == 0 else (r[:, :, 0] + r[:, :, 1], r[:, :, 2])
+                        taps += [cols[0], cols[1]]                            # (ty, tx) order, each [co, ci]
+                    phases.append(torch.stack(taps, 1).reshape(co, 4 * ci))
+            self.w[k] = (torch.stack(phases).to(_f16).contiguous(), None if m.bias is None else m.bias.detach().to(_f32).contiguous())
+        return self.w[k]
+
     def linear(self, m):
         k = id(m)
         if k not in self.w:
@@ -256,6 +279,10 @@ class UNetModel(nn.Module):
             # implicit GEMM: normalise once ([M, C], not 9x) and let TMA fetch the nine shifted windows
             a = x if gn is None else self._norm(pk, x, B, H, W, C, gn, act, xs)[0]
             return A.conv3x3(a, B, H, W, C, w, bias=b, residual=residual, rowbias=rowbias, colstats=colstats), H, W, cs
+        if A.USE_CONV_UP2X and up and stride == 1 and gn is None and cs is None and residual is None and rowbias is None and A.conv3x3_supported(H, W, C):
+            # nearest 2x + 3x3 conv = four 2x2 convs of the low-resolution map (no [M, 9C] gather, 4C instead of 9C per output)
+            w4, b4 = pk.conv_up(conv)
+            return A.conv_up2x(x, B, H, W, C, w4, bias=b4), Ho, Wo, None
         if gn is None:
             a, Ho, Wo = A.norm_act_im2col(x, B, H, W, C, 3, stride, up, None, act)
         else:

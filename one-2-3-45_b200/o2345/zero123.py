@@ -107,8 +107,8 @@ class LatentDiffusion(nn.Module):
 
 @torch.no_grad()
 def sample_model_batch(model, sampler, input_im, xs, ys, n_samples=4, precision='autocast', ddim_eta=1.0, ddim_steps=75,
-                       scale=3.0, h=256, w=256, x_T=None, step_noise=None, decode_chunk=4):
-    """reference utils/zero123_utils.py:60-98; returns images in [0,1], float32, on the host.
+                       scale=3.0, h=256, w=256, x_T=None, step_noise=None, decode_chunk=8, to_host=True):
+    """reference utils/zero123_utils.py:60-98; returns images in [0,1], float32, on the host (to_host=False: on the device).
 
     Beyond the reference: `input_im` may hold G conditioning images; then n_samples views are sampled for EACH of them in
     one batch of G * n_samples (xs / ys list the G * n_samples relative poses, image-major), which is G reference calls
@@ -131,10 +131,9 @@ def sample_model_batch(model, sampler, input_im, xs, ys, n_samples=4, precision=
         samples, _ = sampler.sample(S=ddim_steps, conditioning=cond, batch_size=total, shape=[4, h // 8, w // 8],
                                     verbose=False, unconditional_guidance_scale=scale, unconditional_conditioning=uc,
                                     eta=ddim_eta, x_T=x_T, step_noise=step_noise)
-        # decoded n at a time, as the reference's calls decode them (the up-sampling convolutions gather patches:
-        # 0.3 GB of scratch per image)
         x = torch.cat([model.decode_first_stage(samples[i:i + decode_chunk]) for i in range(0, total, decode_chunk)])
-        return torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0).cpu()
+        x = torch.clamp((x + 1.0) / 2.0, min=0.0, max=1.0)
+        return x.cpu() if to_host else x
 
 
 DELTA_X_1_8 = [0] * 4 + [30] * 4 + [-30] * 4
@@ -145,6 +144,19 @@ DELTA_X_2, DELTA_Y_2 = [-10, 10, 0, 0], [0, 0, -10, 10]
 def _to_uint8(img):
     """(x * 255).astype(uint8): the PNG the reference writes between the stages (zero123_utils.py:125-129)."""
     return (255.0 * img.numpy().transpose(1, 2, 0)).astype(np.uint8)
+
+
+def _to_uint8_device(imgs):
+    """The same quantisation for a batch [n, 3, H, W] that stays on the device: fp32 multiply, truncation -> [n, H, W, 3] uint8."""
+    return (255.0 * imgs.permute(0, 2, 3, 1)).to(torch.uint8).contiguous()
+
+
+def _as_input_device(u8, whiten):
+    """_as_input for device-resident uint8 views [n, H, W, 3] -> [n, 3, H, W] in [-1, 1]."""
+    a = u8.to(torch.float32)
+    if whiten:
+        a = torch.where(a >= 253.0, torch.full_like(a, 255.0), a)
+    return (a / 255.0).permute(0, 3, 1, 2) * 2 - 1
 
 
 def _as_input(u8, whiten):
@@ -161,7 +173,7 @@ def ddim_iterations(ddim_steps, num_timesteps=1000):
 
 @torch.no_grad()
 def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=50, scale=3.0, exp_dir=None, device="cuda",
-                   batched=True):
+                   batched=True, keep_on_device=False):
     """run.py's stage1_run + stage2_run (reference run.py:18-54) with the elevation given instead of estimated: the
     reference's 10 sampler calls (2 x 76 + 8 x 49 UNet iterations at batch 8 = 4 views x CFG).  Returns (stage1 dict
     id -> uint8 image, stage2 dict 'i_j' -> uint8 image, pose dict).  With exp_dir the same PNG files and pose.json are
@@ -173,7 +185,13 @@ def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=
     but every weight is streamed from HBM 125 times instead of 544 and the GEMMs have 2x / 8x the rows.  The noise is
     drawn FIRST, call by call in the reference's order and shapes (x_T, then one tensor per iteration), so every view
     sees exactly the numbers it would have seen in the sequential run.  batched=False runs the ten calls one after the
-    other, as the reference does."""
+    other, as the reference does.
+
+    The views pass through uint8 between the stages and on the way to the reconstruction exactly as the reference's PNG files
+    make them (x * 255 truncated; stage-2 inputs whitened at >= 253), but the quantisation runs on the device and stage 2 is
+    fed from device memory: the host copies (numpy uint8 [H, W, 3], what the dicts hold) are made once at the end -- or not at
+    all with keep_on_device=True (dict values are then uint8 device tensors; `pipeline.image_to_mesh` uses that when no files
+    are to be written)."""
     dev = torch.device(device)
     inp = _as_input(input_u8, False).to(dev)
     stage1, stage2 = {}, {}
@@ -184,18 +202,21 @@ def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=
     def stage1_call(adjust, x_T=None, step_noise=None):
         sampler = DDIMSampler(model)
         imgs = sample_model_batch(model, sampler, inp, [DELTA_X_1_8[i] for i in adjust], [DELTA_Y_1_8[i] for i in adjust],
-                                  n_samples=len(adjust), ddim_steps=ddim_steps, scale=scale, x_T=x_T, step_noise=step_noise)
+                                  n_samples=len(adjust), ddim_steps=ddim_steps, scale=scale, x_T=x_T, step_noise=step_noise,
+                                  to_host=False)
+        u8 = _to_uint8_device(imgs)
         for k, i in enumerate(adjust):
-            stage1[i] = _to_uint8(imgs[k])
+            stage1[i] = u8[k]
 
     def stage2_call(anchors, x_T=None, step_noise=None):
         sampler = DDIMSampler(model)
-        ims = torch.cat([_as_input(stage1[i], True) for i in anchors]).to(dev)
+        ims = _as_input_device(torch.stack([stage1[i] for i in anchors]), True)
         imgs = sample_model_batch(model, sampler, ims, DELTA_X_2 * len(anchors), DELTA_Y_2 * len(anchors), n_samples=4,
-                                  ddim_steps=stage2_steps, scale=scale, x_T=x_T, step_noise=step_noise)
+                                  ddim_steps=stage2_steps, scale=scale, x_T=x_T, step_noise=step_noise, to_host=False)
+        u8 = _to_uint8_device(imgs)
         for a, i in enumerate(anchors):
             for j in range(4):
-                stage2[f"{i}_{j}"] = _to_uint8(imgs[4 * a + j])
+                stage2[f"{i}_{j}"] = u8[4 * a + j]
 
     if not batched:
         stage1_call(first)
@@ -217,13 +238,19 @@ def generate_views(model, input_u8, polar_angle=60, ddim_steps=75, stage2_steps=
         stage1_call(first + second, *gather([("s1", 0), ("s1", 1)], n1))
         anchors = first + second
         stage2_call(anchors, *gather([("s2", i) for i in anchors], n2))
+    if not keep_on_device or exp_dir is not None:
+        host1, host2 = torch.stack([stage1[i] for i in stage1]).cpu().numpy(), torch.stack([stage2[k] for k in stage2]).cpu().numpy()
+        if not keep_on_device:
+            stage1 = {i: host1[n] for n, i in enumerate(stage1)}
+            stage2 = {k: host2[n] for n, k in enumerate(stage2)}
+        files1, files2 = {i: host1[n] for n, i in enumerate(stage1)}, {k: host2[n] for n, k in enumerate(stage2)}
     if exp_dir is not None:
         from PIL import Image
         os.makedirs(os.path.join(exp_dir, "stage1_8"), exist_ok=True)
         os.makedirs(os.path.join(exp_dir, "stage2_8"), exist_ok=True)
-        for i, im in stage1.items():
+        for i, im in files1.items():
             Image.fromarray(im).save(os.path.join(exp_dir, "stage1_8", f"{i}.png"))
-        for k, im in stage2.items():
+        for k, im in files2.items():
             Image.fromarray(im).save(os.path.join(exp_dir, "stage2_8", f"{k}.png"))
         json.dump(pose, open(os.path.join(exp_dir, "pose.json"), "w"), indent=4)
     return stage1, stage2, pose

@@ -284,3 +284,12 @@ def test_batched_views_match_the_sequential_sampler_calls():
     assert float(np.mean(mean)) < 0.4 and worst <= 8, (worst, float(np.mean(mean)))      # measured: 0.135, 2
     # and the views of different anchors are not copies of each other (the per-anchor conditioning reached the batch)
     assert np.abs(out[True][1]["0_0"].astype(np.int32) - out[True][1]["1_0"].astype(np.int32)).mean() > 0.5
+    # device-resident hand-off (what image_to_mesh uses when no files are written): the same uint8 views, never copied to the host
+    torch.manual_seed(11)
+    torch.cuda.manual_seed(11)
+    d1, d2, _ = generate_views(model, img, polar_angle=60, ddim_steps=10, stage2_steps=5, device=dev, batched=True, keep_on_device=True)
+    assert all(v.is_cuda and v.dtype == torch.uint8 and tuple(v.shape) == (256, 256, 3) for v in list(d1.values()) + list(d2.values()))
+    # (GroupNorm group sums are fp32 atomics in shared memory: a last-bit difference may move a pixel across a uint8 boundary)
+    diffs = [np.abs(d1[k].cpu().numpy().astype(np.int32) - out[True][0][k]) for k in d1] + \
+            [np.abs(d2[k].cpu().numpy().astype(np.int32) - out[True][1][k]) for k in d2]
+    assert max(int(d.max()) for d in diffs) <= 2 and float(np.mean([float((d > 0).mean()) for d in diffs])) < 0.02

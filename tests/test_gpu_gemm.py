@@ -263,3 +263,33 @@ def test_persistent_kernel_implicit_conv(persistent_everywhere, B, H, W, C, N):
     assert (out.float() - (conv + emb.float().repeat_interleave(H * W, 0))).abs().max().item() < 2e-2
     out = ops_a.conv3x3(x.view(-1, C), B, H, W, C, wk, bias=bias, residual=res)
     assert (out.float() - (conv + res.float())).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(8, 4, 4, 1280, 1280), (16, 8, 8, 1280, 1280), (64, 16, 16, 640, 640), (4, 32, 32, 512, 512),
+                                       (2, 128, 128, 256, 256), (3, 16, 16, 64, 72)])
+def test_upsampling_conv_as_four_phase_convolutions(B, H, W, C, N):
+    """nearest 2x + 3x3 conv (the UNet / VAE Upsample layers) as four 2x2 implicit convolutions of the low-resolution map with
+    pre-summed weights, against F.interpolate + F.conv2d in fp32 on the same fp16 inputs -- borders (zero padding of the
+    UP-SAMPLED map), every phase, split-K (4x4, 8x8 maps) and persistent (large maps) routes."""
+    from o2345 import ops_a
+    from o2345.unet import _Packed
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + H + C)
+    conv = torch.nn.Conv2d(C, N, 3, padding=1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(N, C, 3, 3, device="cuda", generator=g) * (2.0 / (9 * C)) ** 0.5)
+        conv.bias.copy_(torch.randn(N, device="cuda", generator=g))
+    conv = conv.half()
+    x = (torch.randn(B, H, W, C, device="cuda", generator=g) * 0.5).half()
+    pk = _Packed(conv)
+    w4, b4 = pk.conv_up(conv)
+    out = ops_a.conv_up2x(x.view(-1, C), B, H, W, C, w4, bias=b4)
+    up = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
+    want = torch.nn.functional.conv2d(up, conv.weight.float(), conv.bias.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    assert out.shape == want.shape
+    err = (out.float() - want).abs()
+    assert err.max().item() < 2e-2 and err.mean().item() < 1.5e-3, (err.max().item(), err.mean().item())
+    # the gather route (what round 2 replaced) agrees too
+    a, Ho, Wo = ops_a.norm_act_im2col(x.view(-1, C), B, H, W, C, 3, 1, True, None, False)
+    w9 = conv.weight.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    old = ops_a.gemm(a, w9, bias=conv.bias.float())
+    assert (out.float() - old.float()).abs().max().item() < 2e-2

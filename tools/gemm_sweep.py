@@ -23,9 +23,10 @@ REPS = 6
 lib = L.load()
 net = UNetModel().cuda().requires_grad_(False)
 net.use_cuda_graph = False
-x = torch.randn(8, 8, 32, 32, device="cuda")
-t = torch.full((8,), 501, device="cuda")
-ctx = torch.randn(8, 1, 768, device="cuda")
+BATCH = int(os.environ.get("UNET_BATCH", "8"))
+x = torch.randn(BATCH, 8, 32, 32, device="cuda")
+t = torch.full((BATCH,), 501, device="cuda")
+ctx = torch.randn(BATCH, 1, 768, device="cuda")
 net(x, t, ctx)
 torch.cuda.synchronize()
 

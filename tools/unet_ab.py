@@ -9,12 +9,12 @@ for p in (ROOT, os.path.join(ROOT, "one-2-3-45_b200")):
     sys.path.insert(0, p)
 import numpy as np
 import torch
-from o2345 import _lib
+from o2345 import _lib, ops_a
 from o2345.unet import UNetModel
 lib = _lib.load()
 net = UNetModel().cuda().requires_grad_(False)
-CASES = [("default", {}), ("GEMM never persistent", {"persist": (2, 0)}), ("GroupNorm clusters of 16", {"gn_cl": 16}),
-         ("GroupNorm two kernels", {"gn_one": False}), ("default again", {})]
+CASES = [("default", {}), ("up-sampling convs by gather", {"up2x": False}), ("GEMM never persistent", {"persist": (2, 0)}),
+         ("GroupNorm clusters of 16", {"gn_cl": 16}), ("default again", {})]
 if os.environ.get("UNET_AB_CASES"):
     CASES = eval(os.environ["UNET_AB_CASES"])
 for B in [int(a) for a in sys.argv[1:]] or [16, 64]:
@@ -25,12 +25,13 @@ for B in [int(a) for a in sys.argv[1:]] or [16, 64]:
         lib.o2345_debug_groupnorm_cluster(knobs.get("gn_cl", 0))
         lib.o2345_debug_gemm_force(*knobs.get("force", (0, 0, 0)))
         net.gn_one_kernel = knobs.get("gn_one", True)
+        ops_a.USE_CONV_UP2X = knobs.get("up2x", True)
         net._graphs.clear()
         for _ in range(2):
             net(x, t, ctx)
         torch.cuda.synchronize()
         graphs.append((label, net._graphs[next(iter(net._graphs))], []))
-    lib.o2345_debug_gemm_persist(0, 0); lib.o2345_debug_groupnorm_cluster(0); lib.o2345_debug_gemm_force(0, 0, 0); net.gn_one_kernel = True
+    lib.o2345_debug_gemm_persist(0, 0); lib.o2345_debug_groupnorm_cluster(0); lib.o2345_debug_gemm_force(0, 0, 0); net.gn_one_kernel = True; ops_a.USE_CONV_UP2X = True
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for rnd in range(6):
         for label, g, ts in graphs:
