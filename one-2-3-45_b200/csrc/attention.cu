@@ -93,7 +93,8 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
   float o[NO][4];
 #pragma unroll
   for (int n = 0; n < NO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+  float m0 = -1e30f, m1 = -1e30f;
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};     // running row sums (rows g, g + 8), accumulated by the tensor cores
 
   int it = 0;
   for (int k0 = 0; k0 < N; k0 += KT, ++it) {
@@ -143,21 +144,20 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
     const float a0 = ex2((m0 - mn0) * scale_log2), a1 = ex2((m1 - mn1) * scale_log2);
     m0 = mn0, m1 = mn1;
     const float ms0 = -mn0 * scale_log2, ms1 = -mn1 * scale_log2;
-    float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < KT / 8; ++j) {
-      s[j][0] = ex2(fmaf(s[j][0], scale_log2, ms0)), s[j][1] = ex2(fmaf(s[j][1], scale_log2, ms0));
-      s[j][2] = ex2(fmaf(s[j][2], scale_log2, ms1)), s[j][3] = ex2(fmaf(s[j][3], scale_log2, ms1));
-      r0 += s[j][0] + s[j][1], r1 += s[j][2] + s[j][3];
-    }
-    l0 = l0 * a0 + r0, l1 = l1 * a1 + r1;
 #pragma unroll
     for (int n = 0; n < NO; ++n) o[n][0] *= a0, o[n][1] *= a0, o[n][2] *= a1, o[n][3] *= a1;
-    // ---- O += P V : the S fragments are exactly the A fragments of the next product
+    ls[0] *= a0, ls[1] *= a0, ls[2] *= a1, ls[3] *= a1;
+    // ---- P = 2^(s c - m c), rounded to fp16 into the A fragments of the next product (the S fragments' positions ARE those
+    // fragments' positions); O += P V, and the row sums l += P 1 on the tensor cores too (a B fragment of ones: four MMAs
+    // per tile instead of 32 FADDs per lane and the final cross-lane reduction, and the denominator sums the same rounded
+    // probabilities the numerator uses).  (ex2.approx.f16x2 on packed pairs was tried: it compiles to two MUFU.EX2.F16, no saving.)
 #pragma unroll
     for (int kk = 0; kk < KT / 16; ++kk) {
-      uint32_t pa[4] = {pack2(s[2 * kk][0], s[2 * kk][1]), pack2(s[2 * kk][2], s[2 * kk][3]),
-                        pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+      const uint32_t pa[4] = {pack2(ex2(fmaf(s[2 * kk][0], scale_log2, ms0)), ex2(fmaf(s[2 * kk][1], scale_log2, ms0))),
+                              pack2(ex2(fmaf(s[2 * kk][2], scale_log2, ms1)), ex2(fmaf(s[2 * kk][3], scale_log2, ms1))),
+                              pack2(ex2(fmaf(s[2 * kk + 1][0], scale_log2, ms0)), ex2(fmaf(s[2 * kk + 1][1], scale_log2, ms0))),
+                              pack2(ex2(fmaf(s[2 * kk + 1][2], scale_log2, ms1)), ex2(fmaf(s[2 * kk + 1][3], scale_log2, ms1)))};
+      mma16816(ls, pa, 0x3C003C00u, 0x3C003C00u);
 #pragma unroll
       for (int n = 0; n < NO; ++n) {
         // B fragment of P V: keys 16 kk .. +15 (k) x head dims 8 n .. +7 (n) out of the row-major V tile
@@ -168,8 +168,7 @@ attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k, con
       }
     }
   }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1), l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float l0 = ls[0], l1 = ls[2];   // every column of the ones product holds the row sum: no cross-lane reduction needed
   float i0 = 1.f / l0, i1 = 1.f / l1;
   int row0 = q0 + 16 * warp + g, row1 = row0 + 8;
 #pragma unroll

@@ -366,7 +366,57 @@ __global__ void groupnorm_apply_cluster_kernel(const __half* __restrict__ x, int
   }
 }
 
-// one warp per row: y = (x - mean) * rstd * gamma + beta, fp32 math
+// one warp per row: y = (x - mean) * rstd * gamma + beta, fp32 math.  The row is fetched ONCE with 16-byte loads (a lane keeps up to
+// MAXJ chunks of 8 channels in registers between the statistics and the normalisation) and written with 16-byte stores.
+// (The first version read single halves, twice, and stored single halves: 1.2 TB/s on the batch-64 UNet's 42-168 MB tensors.)
+template <int MAXJ>
+__global__ void layernorm_rows_vec_kernel(const __half* __restrict__ x, int64_t M, int C, float eps, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, __half* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, nch = C >> 3;
+  if (row >= M) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  uint4 v[MAXJ];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < nch) {
+      v[j] = xr[ch];
+      const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        s += f.x + f.y, q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float m = s / C, r = rsqrtf(fmaxf(q / C - m * m, 0.f) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < nch) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * ch)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * ch + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + 8 * ch)), b1 = __ldg(reinterpret_cast<const float4*>(beta + 8 * ch + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
+      __half2 o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        o[e] = __floats2half2_rn((f.x - m) * r * gg[2 * e] + bb[2 * e], (f.y - m) * r * gg[2 * e + 1] + bb[2 * e + 1]);
+      }
+      yr[ch] = *reinterpret_cast<uint4*>(o);
+    }
+  }
+}
+
+// any C (scalar accesses): the fallback for rows that are not whole 16-byte chunks
 __global__ void layernorm_rows_kernel(const __half* __restrict__ x, int64_t M, int C, float eps,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                       __half* __restrict__ y) {
@@ -707,7 +757,16 @@ extern "C" int o2345_norm_act_im2col_stats(const void* x, int B, int H, int W, i
 extern "C" int o2345_layernorm_rows(const void* x, int64_t M, int C, float eps, const float* gamma, const float* beta, void* y,
                                     o2345_stream_t stream) {
   O2345_CHECK_ARG(x && y && gamma && beta, "null pointer");
-  O2345_CUDA(launch_pdl(layernorm_rows_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)(0), ST, (const __half*)x, M, C, eps, gamma, beta, (__half*)y));
+  const bool vec = (C % 8) == 0 && C / 8 <= 160 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)gamma % 16) == 0 &&
+                   ((uintptr_t)beta % 16) == 0;
+  if (vec && C / 8 <= 64)
+    O2345_CUDA(launch_pdl(layernorm_rows_vec_kernel<2>, dim3(cdiv(M, 8)), dim3(256), (size_t)(0), ST, (const __half*)x, M, C, eps, gamma, beta, (__half*)y));
+  else if (vec && C / 8 <= 96)
+    O2345_CUDA(launch_pdl(layernorm_rows_vec_kernel<3>, dim3(cdiv(M, 8)), dim3(256), (size_t)(0), ST, (const __half*)x, M, C, eps, gamma, beta, (__half*)y));
+  else if (vec)
+    O2345_CUDA(launch_pdl(layernorm_rows_vec_kernel<5>, dim3(cdiv(M, 8)), dim3(256), (size_t)(0), ST, (const __half*)x, M, C, eps, gamma, beta, (__half*)y));
+  else
+    O2345_CUDA(launch_pdl(layernorm_rows_kernel, dim3(cdiv(M, 8)), dim3(256), (size_t)(0), ST, (const __half*)x, M, C, eps, gamma, beta, (__half*)y));
   O2345_LAUNCH_CHECK();
   return O2345_OK;
 }

@@ -293,3 +293,18 @@ def test_upsampling_conv_as_four_phase_convolutions(B, H, W, C, N):
     w9 = conv.weight.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
     old = ops_a.gemm(a, w9, bias=conv.bias.float())
     assert (out.float() - old.float()).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (257, 1280), (77, 1024), (50, 768), (33, 72), (9, 100)])
+def test_layernorm_rows_matches_torch(M, C):
+    """16-byte vectorised rows (2 / 3 / 5 chunks per lane) and the scalar fallback (C not a multiple of 8), fp32 statistics."""
+    from o2345 import ops_a
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    x = (torch.randn(M, C, device="cuda", generator=g) * 2.0 + 0.5).half()
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    out = ops_a.layernorm(x, gamma, beta, eps=1e-5)
+    want = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    assert out.dtype == torch.float16 and out.shape == x.shape
+    assert (out.float() - want).abs().max().item() < 1.5e-2          # fp16 output rounding on values up to ~10
+    assert (out.float() - want).abs().mean().item() < 1e-3
