@@ -56,9 +56,10 @@ FLOP_SDF_FWD = 2 * 41856.0
 FLOP_SDF_BWD = 2 * (128 * 144 + 128 * 39)
 RAY_FLOP, RAY_GATHER_BYTES = 211e6, 4.0e6
 # ncu dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one eager UNet forward, by batch (profiles/)
-GEMM_DRAM_BYTES_PER_ITERATION = {8: 2620.6e6, 16: 3751.0e6, 64: 16047.4e6}
-GEMM_DRAM_NOTE = ("ncu launch lists of one eager UNet iteration per batch (profiles/r2_unet_b64_launches_summary.txt, "
-                  "r2_unet_launches_summary.txt): a committed measurement, ncu cannot run inside the bench")
+GEMM_DRAM_BYTES_PER_LAUNCH = {8: 2620.6e6 / 165, 16: 3722.2e6 / 190, 64: 13082.9e6 / 190}
+GEMM_DRAM_NOTE = ("ncu launch lists of one eager UNet iteration per batch (profiles/r2_unet_b64_launches_summary.txt: 13 082.9 MB over the "
+                  "190 gemm_tc launches at batch 64, 3 722.2 MB at batch 16; r2_unet_launches_summary.txt for batch 8): a committed "
+                  "measurement, ncu cannot run inside the bench")
 PUBLISHED_SEC_PER_MESH = 40.0   # BASELINE.md section 1 (reference README.md:154, A6000, whole run.py)
 
 
@@ -280,7 +281,7 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
         # recorded (operands kept alive) and replayed back to back inside ONE CUDA graph, timed with events around the
         # replay -- the kernel's launches exactly as the captured UNet graph issues them, without the glue kernels between.
         rec = []
-        real = {n: getattr(ops_a, n) for n in ("gemm", "bgemm", "conv3x3")}
+        real = {n: getattr(ops_a, n) for n in ("gemm", "bgemm", "conv3x3", "conv_up2x")}
 
         def spy(name):
             def wrap(*a, **k):
@@ -309,6 +310,10 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
                 M, C, N = a[1] * a[2] * a[3], a[4], a[5].shape[0]
                 flops_counted += 2.0 * M * 9 * C * N
                 algo_bytes += 2.0 * (M * C + N * 9 * C) + (2.0 + res) * M * N          # the activation is read once, not nine times
+            elif name == "conv_up2x":                                                  # four 2x2 phase convolutions = four launches
+                M, C, N = a[1] * a[2] * a[3], a[4], a[5].shape[1]
+                flops_counted += 4 * 2.0 * M * 4 * C * N
+                algo_bytes += 2.0 * (M * C + 16 * C * N) + 2.0 * 4 * M * N
             else:
                 flops_counted += 2.0 * a[3] * a[4] * a[8] * a[9] * a[10]
                 algo_bytes += 2.0 * a[3] * a[4] * (a[8] * a[10] + a[9] * a[10] + a[8] * a[9])
@@ -324,7 +329,7 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
         graph.replay()
         torch.cuda.synchronize()
         ms_gemm = float(np.median([ev_time(graph.replay)[0] for _ in range(10)]))
-        n = len(rec)
+        n = sum(4 if name == "conv_up2x" else 1 for name, a, k in rec)
         del graph, rec
         beat("stage breakdown: UNet iteration at batch %d: %.3f ms; its %d GEMM launches replay in %.3f ms (%.0f TFLOP/s)"
              % (B, ms_unet, n, ms_gemm, flops_counted / ms_gemm / 1e9))
@@ -362,7 +367,7 @@ def stage_breakdown(z123, tr, dev, pk, world=1):
     roofline = {"kernel": "gemm_tc_kernel<BN, STAGES, CTAS, MODE> (tcgen05.mma kind::f16, cta_group::2 pairs; all %d GEMM / implicit-conv "
                           "launches of one UNet iteration at batch %d, the batch of the 49 stage-2 iterations)" % (n_gemm, B_TOP),
                 "bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
-                "traffic": GEMM_DRAM_BYTES_PER_ITERATION.get(B_TOP, 0.0) / max(n_gemm, 1) or None,
+                "traffic": GEMM_DRAM_BYTES_PER_LAUNCH.get(B_TOP),
                 "traffic_unit": "bytes of DRAM traffic per launch (mean)",
                 "traffic_note": GEMM_DRAM_NOTE, "algorithmic_bytes_per_launch": algo_bytes / max(n_gemm, 1),
                 "flops_per_step": flops_counted, "gemm_ms_per_unet_iteration": ms_gemm,
