@@ -160,7 +160,7 @@ def last_error() -> str:
 
 
 # kernels launched per successful entry-point call (memsets are not counted)
-_KERNELS_PER_CALL = {"o2345_compact": 3, "o2345_sp_coarsen": 3, "o2345_mc_tri_offsets": 4}
+_KERNELS_PER_CALL = {"o2345_compact": 3, "o2345_sp_coarsen": 3, "o2345_mc_tri_offsets": 4, "o2345_conv_up2x_f16": 4}
 _launches = 0
 
 

@@ -26,6 +26,10 @@ def _p(t, dtype=None):
         return None
     if not t.is_cuda:
         raise L.O2345Error("expected a CUDA tensor (the o2345 kernels have no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # the C-ABI launches on the current device's current stream: a tensor of another GPU would be read through a pointer that
+        # is not valid there (wrap the call in `with torch.cuda.device(t.device)`, as one process per GPU does by construction)
+        raise L.O2345Error(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}")
     if dtype is not None and t.dtype != dtype:
         raise L.O2345Error(f"expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():

@@ -18,7 +18,13 @@ _f16, _f32 = torch.float16, torch.float32
 
 
 def _v(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Raw device pointer of a tensor for the C-ABI (None stays NULL).  No CPU path and no cross-device launches: the library
+    runs on the current device's current stream."""
+    if t is None:
+        return None
+    if not t.is_cuda or t.device.index != torch.cuda.current_device():
+        raise L.O2345Error(f"expected a tensor on the current CUDA device, got one on {t.device}")
+    return C.c_void_p(t.data_ptr())
 
 
 _WS = {}

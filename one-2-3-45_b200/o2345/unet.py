@@ -211,7 +211,7 @@ class UNetModel(nn.Module):
         self._packed = None
         self.use_cuda_graph = True
         self._graphs = {}
-        self._ctx_ref, self._ctx_ver, self._cross_out = None, None, {}
+        self._ctx_ref, self._ctx_ver, self._ctx_pk, self._cross_out = None, None, None, {}
         # GroupNorm statistics tables filled by the producing GEMMs' epilogues (one arena, zeroed once per pass).  OFF by
         # default: measured on a B200 the fused pass is SLOWER (captured UNet graph 5.69 ms with 324 kernels against 4.88 ms
         # with 370): the epilogues' red.add.f32 hit each (image, channel) address from 32 row slabs, and the L2 atomic units
@@ -338,11 +338,12 @@ class UNetModel(nn.Module):
     def _ensure_context(self, context):
         """Single-token cross-attention depends on the context only: out = to_out(to_v(ctx)), constant over the image and
         over every DDIM step of a sampling call.  It is computed once per context TENSOR OBJECT (identity + version; a
-        strong reference is kept so the address cannot be recycled) into static buffers the captured graph reads."""
+        strong reference is kept so the address cannot be recycled) AND per set of packed weights (reloading a checkpoint
+        while the same context tensor is reused must not keep the old projection) into static buffers the captured graph reads."""
         B, T = context.shape[0], context.shape[1]
-        if T != 1 or (context is self._ctx_ref and context._version == self._ctx_ver):
-            return
         pk = self._pk()
+        if T != 1 or (context is self._ctx_ref and context._version == self._ctx_ver and self._ctx_pk == pk.key):
+            return
         ctx16 = context.reshape(B, -1).to(_f16).contiguous()
         for st in (m for m in self.modules() if isinstance(m, SpatialTransformer)):
             attn = st.transformer_blocks[0].attn2
@@ -352,7 +353,7 @@ class UNetModel(nn.Module):
             if key not in self._cross_out:
                 self._cross_out[key] = torch.empty(B, wo.shape[0], dtype=_f16, device=context.device)
             A.gemm(A.gemm(ctx16, wv), wo, bias=bo, out=self._cross_out[key])
-        self._ctx_ref, self._ctx_ver = context, context._version
+        self._ctx_ref, self._ctx_ver, self._ctx_pk = context, context._version, pk.key
 
     def _cross_attention(self, pk, st, blk, h, ctx16, B, N, C):
         attn = blk.attn2
