@@ -148,3 +148,41 @@ def test_ddim_iteration_counts():
     """76 / 49 UNet iterations for S = 75 / 50 (reference ddim.py:126-131 drops the schedule's last entry)."""
     from o2345.zero123 import ddim_iterations
     assert ddim_iterations(75) == 76 and ddim_iterations(50) == 49 and ddim_iterations(5) == 4
+
+
+def test_upsample_conv_weight_decomposition_is_exact_algebra():
+    """nearest 2x + 3x3 conv (pad 1) == four 2x2 convolutions of the low-resolution map with the collapsed kernel rows / columns
+    summed (o2345.unet._Packed.conv_up, consumed by o2345_conv_up2x_f16): checked in fp64 on the CPU with torch's own conv2d,
+    borders included.  Phase (a, b) writes output pixels (2y + a, 2x + b); its tap (ty, tx) reads input (y + ty + a - 1,
+    x + tx + b - 1)."""
+    import torch
+    import torch.nn.functional as F
+    from o2345.unet import _Packed
+    g = torch.Generator().manual_seed(3)
+    C, N, H, W = 8, 5, 6, 7
+    conv = torch.nn.Conv2d(C, N, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(N, C, 3, 3, generator=g))
+        conv.bias.copy_(torch.randn(N, generator=g))
+    x = torch.randn(2, C, H, W, generator=g, dtype=torch.float64)
+    want = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), conv.weight.double(), conv.bias.double(), padding=1)
+    pk = _Packed(conv)
+    w4, b4 = pk.conv_up(conv)
+    assert w4.shape == (4, N, 4 * C) and w4.dtype == torch.float16 and torch.equal(b4, conv.bias.detach().float())
+    # the packed fp16 sums against the same sums in fp64: only the final rounding separates them
+    w = conv.weight.detach().double()
+    rows = {0: (w[:, :, 0], w[:, :, 1] + w[:, :, 2]), 1: (w[:, :, 0] + w[:, :, 1], w[:, :, 2])}
+    got = torch.empty_like(want)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in (0, 1):
+        for b in (0, 1):
+            k = torch.empty(N, C, 2, 2, dtype=torch.float64)
+            for ty in (0, 1):
+                r = rows[a][ty]
+                cols = (r[:, :, 0], r[:, :, 1] + r[:, :, 2]) if b == 0 else (r[:, :, 0] + r[:, :, 1], r[:, :, 2])
+                k[:, :, ty, 0], k[:, :, ty, 1] = cols
+            packed = w4[2 * a + b].double().reshape(N, 2, 2, C).permute(0, 3, 1, 2)          # (ty, tx, c) order -> [N, C, 2, 2]
+            assert float((packed - k).abs().max()) <= 2.0 ** -10 * float(k.abs().max())      # fp16 rounding of the sums
+            full = F.conv2d(xp, k, conv.bias.double())                                        # [.., H + 1, W + 1] over the padded map
+            got[:, :, a::2, b::2] = full[:, :, a:a + H, b:b + W]
+    assert float((got - want).abs().max()) < 1e-10
